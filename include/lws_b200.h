@@ -1,0 +1,141 @@
+/* lws_b200.h -- C-ABI of the B200-native LWS phase-recovery library (liblws_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of Jonathan-LeRoux/lws.  The reference's
+ * own native boundary is the nine `void f(double *Sr, double *Si, double *wr, ...)` functions
+ * that python/lwslib.pxd:1-13 binds out of lwslib/lwslib.h:6-26 (in-place, split re/im
+ * planes, caller-owned host buffers, no error channel), driven by the three binding
+ * functions python/lws.pyx:209-258 (batch_lws), 261-311 (nofuture_lws), 314-375 (online_lws).
+ * On a GPU the unit of work has to be a whole call on a whole batch of utterances, so each
+ * entry point below replaces one *binding function* (the pre/post-processing included:
+ * extspec, |.|, mean, threshold scaling, variant dispatch, crop) rather than one sweep.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; every function returns 0 on success or a negative
+ *     lwsb_status; nothing throws across the boundary; lwsb_last_error() gives the text.
+ *   - host pointers are never retained; device state lives in the context.
+ *   - spectrograms are row-major (T, Nreal) like the reference (python/lws.pyx:221-222),
+ *     element type selected by `kind`: LWSB_C128 = interleaved re,im doubles (numpy
+ *     complex128), LWSB_F64 = real doubles (a magnitude spectrogram; imaginary part 0).
+ *   - weights are (Qprime, Q, L+1) row-major fp64 re / im planes exactly as
+ *     python/lws.pyx:227-228 hands them to the C core; the |W| > 1e-12 mask
+ *     (lws.pyx:231-232) is rebuilt inside.
+ *   - all arithmetic is IEEE fp64 (the reference's type; fp32 cannot hold the 1e-5 parity
+ *     bound).
+ *   - there is NO CPU fallback: without a CUDA device lwsb_create() fails.
+ */
+#ifndef LWS_B200_H_INCLUDED
+#define LWS_B200_H_INCLUDED
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lwsb_ctx lwsb_ctx;
+
+typedef enum {
+    LWSB_OK = 0,
+    LWSB_ERR_CUDA = -1,        /* CUDA runtime / driver failure (text in lwsb_last_error)      */
+    LWSB_ERR_ARG = -2,         /* bad argument (NULL, negative size, unknown enum)              */
+    LWSB_ERR_EVEN_NREAL = -3,  /* Nreal even: reference raises ValueError (lws.pyx:223-224)     */
+    LWSB_ERR_UNSUPPORTED = -4, /* Qprime != Q / use_simplifications=False (*fractionalQ paths)  */
+    LWSB_ERR_STATE = -5,       /* call order: weights or spectrograms not loaded                */
+    LWSB_ERR_NOMEM = -6
+} lwsb_status;
+
+enum { LWSB_C128 = 0, LWSB_F64 = 1 };           /* element kind of a spectrogram buffer        */
+enum { LWSB_W = 0, LWSB_W_AI = 1, LWSB_W_AF = 2 }; /* weight sets (lws.pyx:426-429)             */
+enum { LWSB_HOST = 0, LWSB_DEVICE = 1 };        /* where the caller's buffers live             */
+
+/* flags for the compute calls */
+enum {
+    LWSB_FORCE_GENERIC = 1, /* use the generic wavefront kernels even where a tuned one exists  */
+    LWSB_FORCE_ANYQ = 2     /* use the anyQ formulas for Q = 2 / 4 (debug: variant equivalence) */
+};
+
+/* ---- library / context ------------------------------------------------------------- */
+int lwsb_version(void);                      /* 10000*major + 100*minor + patch               */
+const char *lwsb_last_error(const lwsb_ctx *ctx); /* ctx may be NULL: error of the last failed
+                                                lwsb_create() on this thread                  */
+/* `stream` is a cudaStream_t to launch on (e.g. the caller's current stream) or NULL to let
+ * the context create its own non-blocking stream. */
+int lwsb_create(int device, void *stream, lwsb_ctx **out);
+int lwsb_destroy(lwsb_ctx *ctx);
+int lwsb_sync(lwsb_ctx *ctx);                /* wait for everything queued on the stream       */
+
+/* ---- weights: replaces the Wr/Wi/Wflag marshalling of lws.pyx:227-232, 341-352 -------- */
+int lwsb_set_weights(lwsb_ctx *ctx, int which, const double *wr, const double *wi, int Qprime, int Q, int L);
+
+/* create_weights (lws.pyx:160-181) on the host side of the library: writes (Qprime,Q,L+1)
+ * re / im planes; Qprime = Q when fshift divides T and use_summarized_weights, else T. */
+int lwsb_create_weights(const double *awin, const double *swin, int T, int fshift, int L,
+                        int use_summarized_weights, double *wr, double *wi, int *Qprime_out, int *Q_out);
+
+/* ---- staged interface: keep a batch of utterances resident in HBM ----------------------
+ * lwsb_load     : B spectrograms (T[b], Nreal) -> extended spectrogram (extspec, lws.pyx:146-157,
+ *                 235-237), amplitude plane and mean amplitude (lws.pyx:239-240) on the device.
+ *                 Needs LWSB_W to be set (it fixes Q and L).
+ * lwsb_batch / lwsb_nofuture / lwsb_online : the iteration loops of lws.pyx:244-253,
+ *                 297-306, 365-370 on the resident batch, in place.  `thresholds` are the
+ *                 UNSCALED values (get_thresholds, lws.pyx:203-206); they are multiplied by
+ *                 each utterance's mean amplitude inside, as lws.pyx:245,298,361 do.
+ *                 iterations == 0 is a no-op (lws.pyx:219-220).
+ *                 lwsb_nofuture uses the set selected by `which` (the class passes W_ai,
+ *                 lws.pyx:475).  lwsb_online needs all three sets.
+ * lwsb_store    : crop + recombine (lws.pyx:256) -> B complex128 (T[b], Nreal) arrays.
+ */
+int lwsb_load(lwsb_ctx *ctx, const void *const *S_in, const int *T, int B, int Nreal, int kind, int where);
+int lwsb_batch(lwsb_ctx *ctx, const double *thresholds, int iterations, int flags);
+int lwsb_nofuture(lwsb_ctx *ctx, int which, const double *thresholds, int iterations, int flags);
+int lwsb_online(lwsb_ctx *ctx, const double *thresholds, int iterations, int look_ahead, int flags);
+int lwsb_store(lwsb_ctx *ctx, void *const *S_out, int where);
+
+/* ---- one-shot interface: one call == one reference binding call on B utterances --------
+ * (host or device buffers in, complex128 out; synchronous on return) */
+int lwsb_batch_lws(lwsb_ctx *ctx, const void *const *S_in, void *const *S_out, const int *T, int B, int Nreal,
+                   int kind, int where, const double *thresholds, int iterations, int flags);
+int lwsb_nofuture_lws(lwsb_ctx *ctx, int which, const void *const *S_in, void *const *S_out, const int *T, int B,
+                      int Nreal, int kind, int where, const double *thresholds, int iterations, int flags);
+int lwsb_online_lws(lwsb_ctx *ctx, const void *const *S_in, void *const *S_out, const int *T, int B, int Nreal,
+                    int kind, int where, const double *thresholds, int iterations, int look_ahead, int flags);
+/* run_lws (lws.pyx:495-499): nofuture(W_ai) -> online -> batch without leaving the device.
+ * The ghost frames / mean amplitude are re-derived between the stages exactly as the three
+ * chained reference calls do. */
+int lwsb_run_lws(lwsb_ctx *ctx, const void *const *S_in, void *const *S_out, const int *T, int B, int Nreal,
+                 int kind, int where, const double *nofuture_thr, int nofuture_it, const double *online_thr,
+                 int online_it, int look_ahead, const double *batch_thr, int batch_it, int flags);
+
+/* ---- stft / istft (lws.pyx:43-90, 93-137), batched over signals of equal length ---------
+ * x: (B, nsamples) real; S: (B, M, fftsize/2+1) complex128.  perfectrec padding as the
+ * reference; M and the output length are returned by the *_shape helpers. */
+int lwsb_stft_frames(int nsamples, int fsize, int fshift, int perfectrec);
+int lwsb_istft_length(int M, int fsize, int fshift, int perfectrec);
+int lwsb_stft(lwsb_ctx *ctx, const double *x, int B, int nsamples, const double *awin, int fsize, int fshift,
+              int fftsize, int perfectrec, void *S_out, int where);
+int lwsb_istft(lwsb_ctx *ctx, const void *S_in, int B, int M, int Nreal, const double *swin, int fshift,
+               int perfectrec, double *x_out, int where);
+
+/* ---- introspection used by bench.py / tests -------------------------------------------- */
+/* device time (ms, CUDA events on the context's stream) of the compute kernels of the last
+ * lwsb_batch / lwsb_nofuture / lwsb_online call, and how many kernels it launched. */
+int lwsb_last_compute_ms(lwsb_ctx *ctx, float *ms);
+long long lwsb_launch_count(const lwsb_ctx *ctx); /* kernels launched by this context so far */
+int lwsb_device_info(lwsb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, long long *hbm_bytes);
+/* per-utterance statistics of the resident batch (mean / max of |S|, lws.pyx:240) */
+int lwsb_get_stats(lwsb_ctx *ctx, double *mean_amp, double *max_amp);
+
+/* Host-side mirrors of the device schedule, exported so that the CPU test-suite can replay
+ * the exact dependency order without a GPU (tests/test_schedule.py).  No device needed.
+ *  - lwsb_debug_terms: the linear stencil  acc = sum_e coef[e] * E[m+dr[e]][n+dk[e]]  that the
+ *    kernels use for (weights, Q, L, fold, rframe, cframe, residue p); returns the count.
+ *  - lwsb_debug_online_task: decode position j of the TF_RTISI_LA chain (lwslib.cpp:1432-1491)
+ *    into (row, weight set, rframe, cframe, threshold index or -1). */
+int lwsb_debug_terms(const double *wr, const double *wi, int Q, int L, int fold, int rframe, int cframe, int p,
+                     int max_terms, int *dr, int *dk, double *cr, double *ci);
+long long lwsb_debug_online_chain_length(int T, int iterations, int look_ahead);
+int lwsb_debug_online_task(int T, int iterations, int look_ahead, int Q, long long j, int *row, int *which,
+                           int *rframe, int *cframe, int *thr_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LWS_B200_H_INCLUDED */

@@ -1,0 +1,269 @@
+"""ctypes binding of liblws_b200.so (include/lws_b200.h).  Thin by design: argument
+marshalling and error-code -> exception translation only; there is no Python/numpy compute
+path behind it -- if the CUDA library is missing or no GPU is present, calls raise."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblws_b200.so")
+
+C128, F64 = 0, 1
+W, W_AI, W_AF = 0, 1, 2
+HOST, DEVICE = 0, 1
+FORCE_GENERIC, FORCE_ANYQ = 1, 2
+
+ERR_CUDA, ERR_ARG, ERR_EVEN_NREAL, ERR_UNSUPPORTED, ERR_STATE, ERR_NOMEM = -1, -2, -3, -4, -5, -6
+
+_vp, _dp, _ip = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+_vpp = ctypes.POINTER(ctypes.c_void_p)
+_ci, _cd, _ll = ctypes.c_int, ctypes.c_double, ctypes.c_longlong
+
+# name -> (restype, argtypes): every symbol include/lws_b200.h declares
+SIGNATURES = {
+    "lwsb_version": (_ci, []),
+    "lwsb_last_error": (ctypes.c_char_p, [_vp]),
+    "lwsb_create": (_ci, [_ci, _vp, _vpp]),
+    "lwsb_destroy": (_ci, [_vp]),
+    "lwsb_sync": (_ci, [_vp]),
+    "lwsb_set_weights": (_ci, [_vp, _ci, _dp, _dp, _ci, _ci, _ci]),
+    "lwsb_create_weights": (_ci, [_dp, _dp, _ci, _ci, _ci, _ci, _dp, _dp, _ip, _ip]),
+    "lwsb_load": (_ci, [_vp, _vpp, _ip, _ci, _ci, _ci, _ci]),
+    "lwsb_batch": (_ci, [_vp, _dp, _ci, _ci]),
+    "lwsb_nofuture": (_ci, [_vp, _ci, _dp, _ci, _ci]),
+    "lwsb_online": (_ci, [_vp, _dp, _ci, _ci, _ci]),
+    "lwsb_store": (_ci, [_vp, _vpp, _ci]),
+    "lwsb_batch_lws": (_ci, [_vp, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _ci]),
+    "lwsb_nofuture_lws": (_ci, [_vp, _ci, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _ci]),
+    "lwsb_online_lws": (_ci, [_vp, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _ci, _ci]),
+    "lwsb_run_lws": (_ci, [_vp, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _dp, _ci, _ci, _dp, _ci, _ci]),
+    "lwsb_stft_frames": (_ci, [_ci, _ci, _ci, _ci]),
+    "lwsb_istft_length": (_ci, [_ci, _ci, _ci, _ci]),
+    "lwsb_stft": (_ci, [_vp, _vp, _ci, _ci, _dp, _ci, _ci, _ci, _ci, _vp, _ci]),
+    "lwsb_istft": (_ci, [_vp, _vp, _ci, _ci, _ci, _dp, _ci, _ci, _vp, _ci]),
+    "lwsb_last_compute_ms": (_ci, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "lwsb_launch_count": (_ll, [_vp]),
+    "lwsb_device_info": (_ci, [_vp, _ip, _ip, _ip, ctypes.POINTER(_ll)]),
+    "lwsb_get_stats": (_ci, [_vp, _dp, _dp]),
+    "lwsb_debug_terms": (_ci, [_dp, _dp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ip, _ip, _dp, _dp]),
+    "lwsb_debug_online_chain_length": (_ll, [_ci, _ci, _ci]),
+    "lwsb_debug_online_task": (_ci, [_ci, _ci, _ci, _ci, _ll, _ip, _ip, _ip, _ip, _ip]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load the CUDA library; fail loudly when it has not been built (no fallback)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    "lws_b200: %s is missing -- build it with `python -m lws_b200.build` "
+                    "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+            L = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(L, name)  # AttributeError if the .so does not export it
+                fn.restype, fn.argtypes = res, args
+            _lib = L
+    return _lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _check(code, handle=None):
+    if code >= 0:
+        return code
+    msg = lib().lwsb_last_error(handle)
+    msg = msg.decode() if msg else "error %d" % code
+    if code == ERR_EVEN_NREAL:
+        raise ValueError(msg)
+    if code == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if code == ERR_ARG:
+        raise ValueError("lws_b200: " + msg)
+    raise RuntimeError("lws_b200: " + msg)
+
+
+def create_weights(awin, swin, fshift, L, use_summarized_weights=True):
+    """lws.pyx:160-181 through the library's host-side C++ (no device needed)."""
+    awin = np.ascontiguousarray(awin, dtype=np.float64)
+    swin = np.ascontiguousarray(swin, dtype=np.float64)
+    T = len(awin)
+    qp, q = _ci(0), _ci(0)
+    _check(lib().lwsb_create_weights(_dptr(awin), _dptr(swin), T, int(fshift), int(L), int(bool(use_summarized_weights)),
+                                     None, None, ctypes.byref(qp), ctypes.byref(q)))
+    wr = np.empty((qp.value, q.value, L + 1))
+    wi = np.empty_like(wr)
+    _check(lib().lwsb_create_weights(_dptr(awin), _dptr(swin), T, int(fshift), int(L), int(bool(use_summarized_weights)),
+                                     _dptr(wr), _dptr(wi), None, None))
+    return wr + 1j * wi
+
+
+def _ptr_array(arrays):
+    return (ctypes.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+
+
+class Context(object):
+    """One CUDA device + stream + resident batch (lwsb_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        h = ctypes.c_void_p()
+        _check(lib().lwsb_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._wkeys = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().lwsb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _c(self, code):
+        return _check(code, self._h)
+
+    # -- weights ------------------------------------------------------------------------
+    def set_weights(self, which, Wc):
+        Wc = np.asarray(Wc)
+        if Wc.ndim != 3:
+            raise ValueError("weights must have shape (Qprime, Q, L+1)")
+        key = (Wc.shape, Wc.tobytes())
+        if self._wkeys.get(which) == key:
+            return
+        wr = np.ascontiguousarray(Wc.real, dtype=np.float64)
+        wi = np.ascontiguousarray(Wc.imag, dtype=np.float64)
+        self._c(lib().lwsb_set_weights(self._h, which, _dptr(wr), _dptr(wi), Wc.shape[0], Wc.shape[1], Wc.shape[2] - 1))
+        self._wkeys[which] = key
+
+    # -- staged interface -----------------------------------------------------------------
+    def load(self, arrays, kind):
+        T = np.ascontiguousarray([a.shape[0] for a in arrays], dtype=np.intc)
+        self._T, self._Nreal = T, arrays[0].shape[1]
+        self._c(lib().lwsb_load(self._h, _ptr_array(arrays), T.ctypes.data_as(_ip), len(arrays), self._Nreal, kind, HOST))
+
+    def load_device(self, ptrs, T, Nreal, kind):
+        T = np.ascontiguousarray(T, dtype=np.intc)
+        self._T, self._Nreal = T, int(Nreal)
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        self._c(lib().lwsb_load(self._h, arr, T.ctypes.data_as(_ip), len(ptrs), int(Nreal), kind, DEVICE))
+
+    @staticmethod
+    def _thr(thresholds):
+        t = np.ascontiguousarray(thresholds, dtype=np.float64)
+        return t, (_dptr(t) if len(t) else None), len(t)
+
+    def batch(self, thresholds, flags=0):
+        t, p, n = self._thr(thresholds)
+        self._c(lib().lwsb_batch(self._h, p, n, flags))
+
+    def nofuture(self, which, thresholds, flags=0):
+        t, p, n = self._thr(thresholds)
+        self._c(lib().lwsb_nofuture(self._h, which, p, n, flags))
+
+    def online(self, thresholds, look_ahead, flags=0):
+        t, p, n = self._thr(thresholds)
+        self._c(lib().lwsb_online(self._h, p, n, int(look_ahead), flags))
+
+    def store(self, outs=None):
+        if outs is None:
+            outs = [np.empty((int(t), self._Nreal), dtype=np.complex128) for t in self._T]
+        self._c(lib().lwsb_store(self._h, _ptr_array(outs), HOST))
+        return outs
+
+    def store_device(self, ptrs):
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        self._c(lib().lwsb_store(self._h, arr, DEVICE))
+
+    def sync(self):
+        self._c(lib().lwsb_sync(self._h))
+
+    # -- one-shot interface ---------------------------------------------------------------
+    def _io(self, arrays, outs):
+        T = np.ascontiguousarray([a.shape[0] for a in arrays], dtype=np.intc)
+        if outs is None:
+            outs = [np.empty(a.shape, dtype=np.complex128) for a in arrays]
+        return T, outs
+
+    def batch_lws(self, arrays, kind, thresholds, flags=0, outs=None):
+        T, outs = self._io(arrays, outs)
+        t, p, n = self._thr(thresholds)
+        self._c(lib().lwsb_batch_lws(self._h, _ptr_array(arrays), _ptr_array(outs), T.ctypes.data_as(_ip), len(arrays),
+                                     arrays[0].shape[1], kind, HOST, p, n, flags))
+        return outs
+
+    def nofuture_lws(self, which, arrays, kind, thresholds, flags=0, outs=None):
+        T, outs = self._io(arrays, outs)
+        t, p, n = self._thr(thresholds)
+        self._c(lib().lwsb_nofuture_lws(self._h, which, _ptr_array(arrays), _ptr_array(outs), T.ctypes.data_as(_ip),
+                                        len(arrays), arrays[0].shape[1], kind, HOST, p, n, flags))
+        return outs
+
+    def online_lws(self, arrays, kind, thresholds, look_ahead, flags=0, outs=None):
+        T, outs = self._io(arrays, outs)
+        t, p, n = self._thr(thresholds)
+        self._c(lib().lwsb_online_lws(self._h, _ptr_array(arrays), _ptr_array(outs), T.ctypes.data_as(_ip), len(arrays),
+                                      arrays[0].shape[1], kind, HOST, p, n, int(look_ahead), flags))
+        return outs
+
+    def run_lws(self, arrays, kind, nf_thr, on_thr, look_ahead, b_thr, flags=0, outs=None):
+        T, outs = self._io(arrays, outs)
+        t1, p1, n1 = self._thr(nf_thr)
+        t2, p2, n2 = self._thr(on_thr)
+        t3, p3, n3 = self._thr(b_thr)
+        self._c(lib().lwsb_run_lws(self._h, _ptr_array(arrays), _ptr_array(outs), T.ctypes.data_as(_ip), len(arrays),
+                                   arrays[0].shape[1], kind, HOST, p1, n1, p2, n2, int(look_ahead), p3, n3, flags))
+        return outs
+
+    # -- introspection ----------------------------------------------------------------------
+    def last_compute_ms(self):
+        ms = ctypes.c_float(0)
+        self._c(lib().lwsb_last_compute_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(lib().lwsb_launch_count(self._h))
+
+    def device_info(self):
+        sm, ma, mi, mem = _ci(0), _ci(0), _ci(0), _ll(0)
+        self._c(lib().lwsb_device_info(self._h, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(mem)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), hbm_bytes=mem.value)
+
+    def stats(self):
+        B = len(self._T)
+        mean, mx = np.empty(B), np.empty(B)
+        self._c(lib().lwsb_get_stats(self._h, _dptr(mean), _dptr(mx)))
+        return mean, mx
+
+
+# ---- host-only mirrors of the device schedule (tests) ----------------------------------------
+def debug_terms(Wc, fold, rframe, cframe, p):
+    Wc = np.asarray(Wc)
+    Q, L = Wc.shape[1], Wc.shape[2] - 1
+    wr = np.ascontiguousarray(Wc.real)
+    wi = np.ascontiguousarray(Wc.imag)
+    mx = (2 * Q - 1) * (2 * L + 1)
+    dr, dk = np.zeros(mx, dtype=np.intc), np.zeros(mx, dtype=np.intc)
+    cr, ci = np.zeros(mx), np.zeros(mx)
+    n = _check(lib().lwsb_debug_terms(_dptr(wr), _dptr(wi), Q, L, fold, rframe, cframe, p, mx, dr.ctypes.data_as(_ip),
+                                      dk.ctypes.data_as(_ip), _dptr(cr), _dptr(ci)))
+    return dr[:n], dk[:n], cr[:n] + 1j * ci[:n]
+
+
+def debug_online_chain(T, iterations, look_ahead, Q):
+    n = int(lib().lwsb_debug_online_chain_length(T, iterations, look_ahead))
+    out = []
+    v = [_ci(0) for _ in range(5)]
+    for j in range(n):
+        _check(lib().lwsb_debug_online_task(T, iterations, look_ahead, Q, j, *[ctypes.byref(x) for x in v]))
+        out.append(tuple(x.value for x in v))
+    return out

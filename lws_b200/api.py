@@ -1,0 +1,330 @@
+"""The reference's Python surface (python/lws.pyx:209-499) on top of the CUDA library.
+
+Same names, positional order, defaults and error behaviour as the Cython module, so that
+``import lws_b200 as lws`` is a drop-in for the hot path.  Extensions (keyword-only or
+impossible in the reference, so they cannot collide):
+
+* ``S`` may be a 3-D array ``(B, T, Nreal)`` or a list of 2-D arrays ``(T_i, Nreal)``: the
+  whole batch is processed by one call on the GPU (the reference has no batch dimension).
+* ``device=`` on the class / functions selects the GPU(s); a list shards the utterances over
+  several GPUs (independent utterances, no collective).
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+from . import _native, dsp
+from .dsp import get_thresholds
+
+_EVEN = 'Please only include non-negative frequencies in the input spectrogram.'
+_ctx_lock = threading.Lock()
+_contexts = {}
+
+
+def _context(device):
+    with _ctx_lock:
+        c = _contexts.get(device)
+        if c is None:
+            c = _contexts[device] = _native.Context(device)
+        return c
+
+
+def _devices(device):
+    if device is None:
+        return [0]
+    if isinstance(device, (list, tuple)):
+        return [int(d) for d in device]
+    return [int(device)]
+
+
+def _as_batch(S):
+    """-> (list of 2-D C-contiguous float64/complex128 arrays, kind, rebuild(outs))."""
+    if isinstance(S, (list, tuple)):
+        arrs, shape = [np.asarray(a) for a in S], "list"
+    else:
+        S = np.asarray(S)
+        if S.ndim == 3:
+            arrs, shape = [S[b] for b in range(S.shape[0])], "3d"
+        else:
+            arrs, shape = [S], "2d"
+    if any(a.ndim != 2 for a in arrs):
+        raise ValueError('expected (T, Nreal) spectrograms')
+    cplx = any(np.iscomplexobj(a) for a in arrs)
+    dt = np.complex128 if cplx else np.float64
+    arrs = [np.ascontiguousarray(a, dtype=dt) for a in arrs]
+    return arrs, (_native.C128 if cplx else _native.F64), shape
+
+
+def _rebuild(outs, shape):
+    if shape == "2d":
+        return outs[0]
+    if shape == "3d":
+        return np.stack(outs) if not _is_views_of_one(outs) else outs[0].base
+    return outs
+
+
+def _is_views_of_one(outs):
+    b = outs[0].base
+    return b is not None and b.ndim == 3 and all(o.base is b for o in outs)
+
+
+def _alloc_outs(arrs, shape):
+    if shape == "3d":
+        big = np.empty((len(arrs),) + arrs[0].shape, dtype=np.complex128)
+        return [big[b] for b in range(len(arrs))]
+    return [np.empty(a.shape, dtype=np.complex128) for a in arrs]
+
+
+def _passthrough(S):
+    # iterations == 0: the reference returns the (complex128-cast) input itself (lws.pyx:212-220)
+    if isinstance(S, (list, tuple)):
+        return [a if a.dtype == np.complex128 else a.astype(np.complex128) for a in map(np.asarray, S)]
+    S = np.asarray(S) if not isinstance(S, np.ndarray) else S
+    return S if S.dtype == np.complex128 else S.astype(np.complex128)
+
+
+def _check_shapes(arrs):
+    nreal = arrs[0].shape[1]
+    if any(a.shape[1] != nreal for a in arrs):
+        raise ValueError('all spectrograms of a batch must have the same number of bins')
+    if nreal % 2 == 0:
+        raise ValueError(_EVEN)
+    if any(a.shape[0] < 1 for a in arrs):
+        raise ValueError('empty spectrogram')
+
+
+def _check_weights(W, use_simplifications):
+    if W.shape[0] != W.shape[1] or not use_simplifications:
+        raise NotImplementedError(
+            'per-frequency weights (frame shift not dividing the frame size, or use_simplifications=False: '
+            'the reference\'s *fractionalQ path) are not supported by the CUDA implementation')
+
+
+def _shard(n, k):
+    """contiguous, balanced split of n utterances over k devices"""
+    k = max(1, min(k, n))
+    b = [(n * i) // k for i in range(k + 1)]
+    return [(b[i], b[i + 1]) for i in range(k)]
+
+
+def _run_sharded(devices, arrs, outs, fn):
+    """fn(ctx, arrays, outs) on each device's contiguous share; one host thread per GPU
+    (ctypes releases the GIL, so the GPUs run concurrently)."""
+    parts = _shard(len(arrs), len(devices))
+    if len(parts) == 1:
+        fn(_context(devices[0]), arrs, outs)
+        return
+    errs = []
+
+    def work(dev, lo, hi):
+        try:
+            fn(_context(dev), arrs[lo:hi], outs[lo:hi])
+        except BaseException as e:  # re-raised in the caller
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(devices[i], lo, hi)) for i, (lo, hi) in enumerate(parts)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errs:
+        raise errs[0]
+
+
+def batch_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=0):
+    """Batch-mode LWS phase reconstruction (lws.pyx:209-258)."""
+    if len(thresholds) == 0:
+        return _passthrough(S)
+    arrs, kind, shape = _as_batch(S)
+    _check_shapes(arrs)
+    _check_weights(W, use_simplifications)
+    outs = _alloc_outs(arrs, shape)
+
+    def fn(ctx, a, o):
+        ctx.set_weights(_native.W, W)
+        ctx.batch_lws(a, kind, thresholds, flags, outs=o)
+
+    _run_sharded(_devices(device), arrs, outs, fn)
+    return _rebuild(outs, shape)
+
+
+def nofuture_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=0):
+    """LWS using past frames only, typically for initialisation (lws.pyx:261-311)."""
+    if len(thresholds) == 0:
+        return _passthrough(S)
+    arrs, kind, shape = _as_batch(S)
+    _check_shapes(arrs)
+    _check_weights(W, use_simplifications)
+    outs = _alloc_outs(arrs, shape)
+
+    def fn(ctx, a, o):
+        ctx.set_weights(_native.W, W)
+        ctx.nofuture_lws(_native.W, a, kind, thresholds, flags, outs=o)
+
+    _run_sharded(_devices(device), arrs, outs, fn)
+    return _rebuild(outs, shape)
+
+
+def online_lws(S, W, W_ai, W_af, thresholds, LA, fshift, use_simplifications=True, *, device=None, flags=0):
+    """Online (TF-RTISI-LA) LWS phase reconstruction (lws.pyx:314-375)."""
+    if len(thresholds) == 0:
+        return _passthrough(S)
+    arrs, kind, shape = _as_batch(S)
+    _check_shapes(arrs)
+    _check_weights(W, use_simplifications)
+    outs = _alloc_outs(arrs, shape)
+
+    def fn(ctx, a, o):
+        ctx.set_weights(_native.W, W)
+        ctx.set_weights(_native.W_AI, W_ai)
+        ctx.set_weights(_native.W_AF, W_af)
+        ctx.online_lws(a, kind, thresholds, int(LA), flags, outs=o)
+
+    _run_sharded(_devices(device), arrs, outs, fn)
+    return _rebuild(outs, shape)
+
+
+class lws(object):
+    """Drop-in for ``lws.lws`` (lws.pyx:378-499).  Holds windows, weights and the iteration /
+    threshold schedule; every spectrogram computation runs on the GPU."""
+
+    def __init__(self, awin_or_fsize, fshift, L=5, swin=None, look_ahead=3,
+                 nofuture_iterations=0, nofuture_alpha=1, nofuture_beta=0.1, nofuture_gamma=1,
+                 online_iterations=0, online_alpha=1, online_beta=0.1, online_gamma=1,
+                 batch_iterations=100, batch_alpha=100, batch_beta=0.1, batch_gamma=1,
+                 symmetric_win=True, mode=None, fftsize=None, perfectrec=True, use_simplifications=True,
+                 *, device=None):
+        if isinstance(awin_or_fsize, int):
+            # default perfect-reconstruction window: sqrt-Hann, renormalised (lws.pyx:384-387)
+            awin = np.sqrt(dsp.hann(awin_or_fsize, symmetric=symmetric_win, use_offset=False))
+            awin = np.sqrt(awin * dsp.synthwin(awin, fshift))
+        else:
+            awin = awin_or_fsize
+        if awin.ndim > 1:
+            # the reference compares a shape tuple with an int here (lws.pyx:391), which raises
+            # TypeError for a 2-D window with more than one row; same expression, same behaviour
+            if (awin.ndim > 2) or (awin.shape[0] > 1 and awin.shape > 1):
+                raise ValueError('The analysis window should be flat')
+            else:
+                awin = awin.flatten()
+        if fftsize is None:
+            fftsize = len(awin)
+        if fftsize > len(awin):
+            if (fftsize - len(awin)) % 2 != 0:
+                raise ValueError('The zero-padding should add even length to the original window.')
+            pad_length = (fftsize - len(awin)) // 2
+            print('Zero-padding symmetrically around the original windows.\n'
+                  'WARNING: for code simplicity, a consequence is that the first/last '
+                  '{} samples of the signal will not be '.format(pad_length) +
+                  'in the perfect reconstruction region.')
+            pad = np.zeros(pad_length)
+            awin = np.hstack((pad, awin, pad))
+            if swin is not None:
+                swin = np.hstack((pad, swin, pad))
+
+        self.awin = awin
+        if swin is not None:
+            print('Provided synthesis window is renormalized for perfect reconstruction.')
+        self.swin = dsp.synthwin(awin, fshift, swin=swin)
+        self.fshift = fshift
+        self.fsize = len(awin)
+        self.perfectrec = perfectrec
+        self.L = L
+        if self.fsize % self.fshift == 0:
+            self.Q = int(self.fsize / self.fshift)
+        else:
+            self.Q = self.fsize / self.fshift
+        self.use_simplifications = use_simplifications
+        self.W = dsp.create_weights(self.awin, self.swin, self.fshift, self.L,
+                                    use_summarized_weights=self.use_simplifications)
+        self.win_ai, self.win_af = dsp.build_asymmetric_windows(self.awin * self.swin, self.fshift)
+        self.W_ai = dsp.create_weights(self.win_ai, self.swin, self.fshift, self.L,
+                                       use_summarized_weights=self.use_simplifications)
+        self.W_af = dsp.create_weights(self.win_af, self.swin, self.fshift, self.L,
+                                       use_summarized_weights=self.use_simplifications)
+        self.look_ahead = look_ahead
+
+        if mode == 'speech':
+            nofuture_iterations = 0
+            online_iterations = 0
+        elif mode == 'music':
+            nofuture_iterations = 1
+            online_iterations = 10
+
+        self.batch_iterations = batch_iterations
+        self.batch_alpha = batch_alpha
+        self.batch_beta = batch_beta
+        self.batch_gamma = batch_gamma
+        self.online_iterations = online_iterations
+        self.online_alpha = online_alpha
+        self.online_beta = online_beta
+        self.online_gamma = online_gamma
+        self.nofuture_iterations = nofuture_iterations
+        self.nofuture_alpha = nofuture_alpha
+        self.nofuture_beta = nofuture_beta
+        self.nofuture_gamma = nofuture_gamma
+        self.device = device
+
+        if (not np.allclose(awin, awin[::-1])):
+            print('WARNING: It appears you are using an analysis window that is not symmetric.\n'
+                  'The current code uses simplifications that rely on such symmetry, so the code may not behave properly.')
+
+    # ---- transforms (GPU) -------------------------------------------------------------------
+    def get_consistency(self, S):
+        from . import transforms
+        return transforms.get_consistency(S, self.fsize, self.fshift, self.awin, self.swin,
+                                          perfectrec=self.perfectrec, device=self.device)
+
+    def stft(self, S):
+        from . import transforms
+        return transforms.stft(S, self.fsize, self.fshift, self.awin, perfectrec=self.perfectrec, device=self.device)
+
+    def istft(self, S):
+        from . import transforms
+        # awin is not passed: swin was renormalised at construction (lws.pyx:465-467)
+        return transforms.istft(S, self.fshift, self.swin, perfectrec=self.perfectrec, device=self.device)
+
+    # ---- phase reconstruction (GPU) -----------------------------------------------------------
+    def nofuture_lws(self, S, iterations=None, thresholds=None):
+        if iterations is None:
+            iterations = self.nofuture_iterations
+        if thresholds is None:
+            thresholds = get_thresholds(iterations, self.nofuture_alpha, self.nofuture_beta, self.nofuture_gamma)
+        return nofuture_lws(S, self.W_ai, thresholds, use_simplifications=self.use_simplifications, device=self.device)
+
+    def online_lws(self, S, iterations=None, thresholds=None):
+        if iterations is None:
+            iterations = self.online_iterations
+        if thresholds is None:
+            thresholds = get_thresholds(iterations, self.online_alpha, self.online_beta, self.online_gamma)
+        return online_lws(S, self.W, self.W_ai, self.W_af, thresholds, self.look_ahead, self.fshift,
+                          use_simplifications=self.use_simplifications, device=self.device)
+
+    def batch_lws(self, S, iterations=None, thresholds=None):
+        if iterations is None:
+            iterations = self.batch_iterations
+        if thresholds is None:
+            thresholds = get_thresholds(iterations, self.batch_alpha, self.batch_beta, self.batch_gamma)
+        return batch_lws(S, self.W, thresholds, use_simplifications=self.use_simplifications, device=self.device)
+
+    def run_lws(self, S):
+        """nofuture -> online -> batch (lws.pyx:495-499), fused on the device: the spectrograms
+        cross PCIe once in each direction instead of three times."""
+        nf = get_thresholds(self.nofuture_iterations, self.nofuture_alpha, self.nofuture_beta, self.nofuture_gamma)
+        on = get_thresholds(self.online_iterations, self.online_alpha, self.online_beta, self.online_gamma)
+        ba = get_thresholds(self.batch_iterations, self.batch_alpha, self.batch_beta, self.batch_gamma)
+        if len(nf) + len(on) + len(ba) == 0:
+            return _passthrough(S)
+        arrs, kind, shape = _as_batch(S)
+        _check_shapes(arrs)
+        _check_weights(self.W, self.use_simplifications)
+        outs = _alloc_outs(arrs, shape)
+
+        def fn(ctx, a, o):
+            ctx.set_weights(_native.W, self.W)
+            ctx.set_weights(_native.W_AI, self.W_ai)
+            ctx.set_weights(_native.W_AF, self.W_af)
+            ctx.run_lws(a, kind, nf, on, self.look_ahead, ba, outs=o)
+
+        _run_sharded(_devices(self.device), arrs, outs, fn)
+        return _rebuild(outs, shape)

@@ -1,0 +1,641 @@
+// api.cu -- the extern "C" boundary (include/lws_b200.h) and the host runtime behind it:
+// context, device buffers, stencil cache, stage sequencing.  No torch types, no exceptions
+// across the ABI, no CPU compute path: every entry point that does arithmetic on
+// spectrograms launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/lws_b200.h"
+#include "kernels.h"
+#include "lwsb_common.h"
+#include "stencil.h"
+
+using namespace lwsb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct StencilDev {
+    DevBuf terms, count;
+    int maxt = 0;
+    LwsbStencil view() const { return LwsbStencil{terms.as<const LwsbTerm>(), count.as<const int>(), maxt}; }
+};
+
+} // namespace
+
+struct lwsb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    cudaDeviceProp prop{};
+
+    WeightSet w[3];
+    std::map<std::tuple<int, int, int, int>, StencilDev> stencils; // (which, fold, rframe, cframe)
+
+    // resident batch
+    int B = 0, Nreal = 0, Q = 0, L = 0, P = 0, c0 = 0, maxT = 0;
+    long long total_rows = 0, total_bins = 0;
+    std::vector<int> T;
+    std::vector<long long> rowbase, binbase;
+    DevBuf E, A, row_sum, row_max, mean_amp, max_amp, dT, drowbase, stage, dptr, dthr, dsts, flags;
+    std::vector<void *> hptr;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing_valid = false;
+    long long launches = 0;
+
+    LwsbView view() const
+    {
+        LwsbView v;
+        v.E = E.as<double2>(); v.A = A.as<double>();
+        v.rowbase = drowbase.as<const long long>(); v.T = dT.as<const int>();
+        v.mean_amp = mean_amp.as<const double>();
+        v.P = P; v.c0 = c0; v.Nreal = Nreal; v.L = L; v.Q = Q; v.B = B;
+        return v;
+    }
+};
+
+namespace {
+
+int fail(lwsb_ctx *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, LWSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+#define CHECK_CTX(c) if (!(c)) return LWSB_ERR_ARG
+
+int use_device(lwsb_ctx *c) { CU(c, cudaSetDevice(c->device)); return LWSB_OK; }
+
+int fold_for(int Q, int flags)
+{
+    if (flags & LWSB_FORCE_ANYQ) return LWSB_FOLD_ANY;
+    return Q == 2 ? LWSB_FOLD_Q2 : (Q == 4 ? LWSB_FOLD_Q4 : LWSB_FOLD_ANY); // lws.pyx:246-253
+}
+
+// builds (or fetches) the device copy of a stencil
+int get_stencil(lwsb_ctx *c, int which, int fold, int rframe, int cframe, LwsbStencil *out)
+{
+    auto key = std::make_tuple(which, fold, rframe, cframe);
+    auto it = c->stencils.find(key);
+    if (it == c->stencils.end()) {
+        const WeightSet &w = c->w[which];
+        if (!w.valid()) return fail(c, LWSB_ERR_STATE, "weight set not loaded");
+        const int Q = w.Q, maxt = (2 * Q - 1) * (2 * w.L + 1);
+        std::vector<LwsbTerm> all((size_t)Q * maxt, LwsbTerm{0, 0, 0.0, 0.0});
+        std::vector<int> cnt(Q, 0);
+        for (int p = 0; p < Q; ++p) {
+            std::vector<LwsbTerm> t;
+            build_terms(w, fold, rframe, cframe, p, t);
+            cnt[p] = (int)t.size();
+            std::copy(t.begin(), t.end(), all.begin() + (size_t)p * maxt);
+        }
+        StencilDev sd;
+        sd.maxt = maxt;
+        CU(c, sd.terms.reserve(all.size() * sizeof(LwsbTerm)));
+        CU(c, sd.count.reserve(cnt.size() * sizeof(int)));
+        CU(c, cudaMemcpyAsync(sd.terms.p, all.data(), all.size() * sizeof(LwsbTerm), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(sd.count.p, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream)); // host vectors go out of scope
+        it = c->stencils.emplace(key, sd).first;
+    }
+    *out = it->second.view();
+    return LWSB_OK;
+}
+
+void drop_stencils(lwsb_ctx *c, int which)
+{
+    for (auto it = c->stencils.begin(); it != c->stencils.end();) {
+        if (std::get<0>(it->first) == which) {
+            it->second.terms.release();
+            it->second.count.release();
+            it = c->stencils.erase(it);
+        } else ++it;
+    }
+}
+
+int upload_thresholds(lwsb_ctx *c, const double *thr, int n)
+{
+    CU(c, c->dthr.reserve(std::max(n, 1) * sizeof(double)));
+    if (n > 0) CU(c, cudaMemcpyAsync(c->dthr.p, thr, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return LWSB_OK;
+}
+
+int begin_compute(lwsb_ctx *c)
+{
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    return LWSB_OK;
+}
+int end_compute(lwsb_ctx *c)
+{
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    c->timing_valid = true;
+    return LWSB_OK;
+}
+
+int check_resident(lwsb_ctx *c)
+{
+    if (c->B <= 0) return fail(c, LWSB_ERR_STATE, "no spectrograms loaded (call lwsb_load first)");
+    return LWSB_OK;
+}
+
+} // namespace
+
+// ============================================================================ library / context
+extern "C" int lwsb_version(void) { return 100; }
+
+extern "C" const char *lwsb_last_error(const lwsb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int lwsb_create(int device, void *stream, lwsb_ctx **out)
+{
+    if (!out) return fail(nullptr, LWSB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, LWSB_ERR_CUDA,
+                    std::string("no CUDA device available (this library has no CPU path): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, LWSB_ERR_ARG, "device index out of range");
+    lwsb_ctx *c = new lwsb_ctx();
+    c->device = device;
+    auto bail = [&](const char *what, cudaError_t err) {
+        int code = fail(nullptr, LWSB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err));
+        delete c;
+        return code;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        c->own_stream = true;
+    }
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    *out = c;
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_destroy(lwsb_ctx *c)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 3; ++i) drop_stencils(c, i);
+    for (DevBuf *b : {&c->E, &c->A, &c->row_sum, &c->row_max, &c->mean_amp, &c->max_amp, &c->dT, &c->drowbase,
+                      &c->stage, &c->dptr, &c->dthr, &c->dsts, &c->flags})
+        b->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_sync(lwsb_ctx *c)
+{
+    CHECK_CTX(c);
+    if (int r = use_device(c)) return r;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LWSB_OK;
+}
+
+// ============================================================================ weights
+extern "C" int lwsb_set_weights(lwsb_ctx *c, int which, const double *wr, const double *wi, int Qprime, int Q, int L)
+{
+    CHECK_CTX(c);
+    if (which < 0 || which > 2 || !wr || !wi || Q < 1 || L < 0) return fail(c, LWSB_ERR_ARG, "bad weight arguments");
+    if (Qprime != Q)
+        return fail(c, LWSB_ERR_UNSUPPORTED,
+                    "per-frequency weights (Qprime != Q: the reference's *fractionalQ path) are not supported");
+    if (int r = use_device(c)) return r;
+    WeightSet &w = c->w[which];
+    w.Q = Q; w.L = L;
+    const size_t n = (size_t)Q * Q * (L + 1);
+    w.wr.assign(wr, wr + n);
+    w.wi.assign(wi, wi + n);
+    drop_stencils(c, which);
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_create_weights(const double *awin, const double *swin, int T, int fshift, int L,
+                                   int use_summarized_weights, double *wr, double *wi, int *Qprime_out, int *Q_out)
+{
+    // lws.pyx:160-181
+    if (!awin || !swin || T < 1 || fshift < 1 || L < 0) return LWSB_ERR_ARG;
+    const int Q = (T + fshift - 1) / fshift;
+    const double Qf = (double)T / (double)fshift;
+    const int Qp = (T % fshift == 0 && use_summarized_weights) ? Q : T;
+    if (Qprime_out) *Qprime_out = Qp;
+    if (Q_out) *Q_out = Q;
+    if (!wr || !wi) return LWSB_OK; // shape query
+    const double twopi = 2.0 * M_PI;
+    std::vector<double> w0r((size_t)(L + 1) * Q), w0i((size_t)(L + 1) * Q);
+    for (int k = 0; k <= L; ++k)
+        for (int q = 0; q < Q; ++q) {
+            double sr = 0.0, si = 0.0;
+            for (int t = 0; t < T - q * fshift; ++t) {
+                const double wp = awin[t] * swin[t + q * fshift] / T;
+                const double ang = -twopi * k * t / T;
+                sr += std::cos(ang) * wp;
+                si += std::sin(ang) * wp;
+            }
+            const double ang = -twopi * k * q / Qf;
+            const double cr = std::cos(ang), ci = std::sin(ang);
+            w0r[(size_t)k * Q + q] = sr * cr - si * ci;
+            w0i[(size_t)k * Q + q] = sr * ci + si * cr;
+        }
+    w0r[0] -= 1.0;
+    for (int n = 0; n < Qp; ++n)
+        for (int q = 0; q < Q; ++q) {
+            const double ang = twopi * n * q / Qf;
+            const double cr = std::cos(ang), ci = std::sin(ang);
+            for (int k = 0; k <= L; ++k) {
+                const double a = w0r[(size_t)k * Q + q], b = w0i[(size_t)k * Q + q];
+                wr[((size_t)n * Q + q) * (L + 1) + k] = a * cr - b * ci;
+                wi[((size_t)n * Q + q) * (L + 1) + k] = a * ci + b * cr;
+            }
+        }
+    return LWSB_OK;
+}
+
+// ============================================================================ staged interface
+extern "C" int lwsb_load(lwsb_ctx *c, const void *const *S_in, const int *T, int B, int Nreal, int kind, int where)
+{
+    CHECK_CTX(c);
+    if (!S_in || !T || B < 1 || Nreal < 1 || (kind != LWSB_C128 && kind != LWSB_F64) ||
+        (where != LWSB_HOST && where != LWSB_DEVICE))
+        return fail(c, LWSB_ERR_ARG, "bad lwsb_load arguments");
+    if (Nreal % 2 == 0)
+        return fail(c, LWSB_ERR_EVEN_NREAL, "Please only include non-negative frequencies in the input spectrogram.");
+    if (!c->w[LWSB_W].valid()) return fail(c, LWSB_ERR_STATE, "set LWSB_W before loading spectrograms");
+    if (int r = use_device(c)) return r;
+    c->B = 0; // invalid until everything below succeeded
+    const int Q = c->w[LWSB_W].Q, L = c->w[LWSB_W].L;
+    const int Np = Nreal + 2 * L;
+    const int coff = (4 - L % 4) % 4; // bin 0 lands on a 64-byte boundary
+    const int P = (coff + Np + 3) / 4 * 4;
+    std::vector<long long> rowbase(B), binbase(B);
+    long long rows = 0, bins = 0;
+    int maxT = 0;
+    for (int b = 0; b < B; ++b) {
+        if (T[b] < 1 || !S_in[b]) return fail(c, LWSB_ERR_ARG, "empty utterance in batch");
+        rowbase[b] = rows; binbase[b] = bins;
+        rows += T[b] + 2 * (Q - 1);
+        bins += (long long)T[b] * Nreal;
+        maxT = std::max(maxT, T[b]);
+    }
+    CU(c, c->E.reserve((size_t)rows * P * sizeof(double2)));
+    CU(c, c->A.reserve((size_t)rows * P * sizeof(double)));
+    CU(c, c->row_sum.reserve((size_t)rows * sizeof(double)));
+    CU(c, c->row_max.reserve((size_t)rows * sizeof(double)));
+    CU(c, c->mean_amp.reserve(B * sizeof(double)));
+    CU(c, c->max_amp.reserve(B * sizeof(double)));
+    CU(c, c->dT.reserve(B * sizeof(int)));
+    CU(c, c->drowbase.reserve(B * sizeof(long long)));
+    CU(c, c->dptr.reserve(B * sizeof(void *)));
+    CU(c, cudaMemcpyAsync(c->dT.p, T, B * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->drowbase.p, rowbase.data(), B * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    const size_t esz = kind == LWSB_C128 ? sizeof(double2) : sizeof(double);
+    c->hptr.resize(B);
+    if (where == LWSB_HOST) {
+        CU(c, c->stage.reserve((size_t)bins * sizeof(double2))); // sized for the complex128 output as well
+        for (int b = 0; b < B; ++b) {
+            char *dst = c->stage.as<char>() + (size_t)binbase[b] * esz;
+            CU(c, cudaMemcpyAsync(dst, S_in[b], (size_t)T[b] * Nreal * esz, cudaMemcpyHostToDevice, c->stream));
+            c->hptr[b] = dst;
+        }
+    } else {
+        for (int b = 0; b < B; ++b) c->hptr[b] = const_cast<void *>(S_in[b]);
+    }
+    CU(c, cudaMemcpyAsync(c->dptr.p, c->hptr.data(), B * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+    c->T.assign(T, T + B);
+    c->rowbase = rowbase; c->binbase = binbase;
+    c->Nreal = Nreal; c->Q = Q; c->L = L; c->P = P; c->c0 = coff + L; c->maxT = maxT;
+    c->total_rows = rows; c->total_bins = bins;
+    c->B = B;
+    LwsbView v = c->view();
+    launch_extend(v, kind, c->dptr.as<const void *const>(), c->row_sum.as<double>(), c->row_max.as<double>(),
+                  c->mean_amp.as<double>(), c->max_amp.as<double>(), maxT + 2 * (Q - 1), c->stream);
+    c->launches += 2;
+    CU(c, cudaGetLastError());
+    // rowbase / hptr host vectors are read by the async copies above: make them safe to reuse
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_store(lwsb_ctx *c, void *const *S_out, int where)
+{
+    CHECK_CTX(c);
+    if (!S_out || (where != LWSB_HOST && where != LWSB_DEVICE)) return fail(c, LWSB_ERR_ARG, "bad lwsb_store arguments");
+    if (int r = check_resident(c)) return r;
+    if (int r = use_device(c)) return r;
+    const int B = c->B;
+    if (where == LWSB_HOST) {
+        CU(c, c->stage.reserve((size_t)c->total_bins * sizeof(double2)));
+        for (int b = 0; b < B; ++b) c->hptr[b] = c->stage.as<double2>() + c->binbase[b];
+    } else {
+        for (int b = 0; b < B; ++b) {
+            if (!S_out[b]) return fail(c, LWSB_ERR_ARG, "NULL output pointer");
+            c->hptr[b] = S_out[b];
+        }
+    }
+    CU(c, cudaMemcpyAsync(c->dptr.p, c->hptr.data(), B * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+    launch_crop(c->view(), c->dptr.as<void *const>(), c->maxT, c->stream);
+    c->launches += 1;
+    CU(c, cudaGetLastError());
+    if (where == LWSB_HOST)
+        for (int b = 0; b < B; ++b) {
+            if (!S_out[b]) return fail(c, LWSB_ERR_ARG, "NULL output pointer");
+            CU(c, cudaMemcpyAsync(S_out[b], c->hptr[b], (size_t)c->T[b] * c->Nreal * sizeof(double2),
+                                  cudaMemcpyDeviceToHost, c->stream));
+        }
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations, int flags)
+{
+    CHECK_CTX(c);
+    if (iterations < 0 || (iterations > 0 && !thresholds)) return fail(c, LWSB_ERR_ARG, "bad thresholds");
+    if (int r = check_resident(c)) return r;
+    if (iterations == 0) return LWSB_OK; // lws.pyx:219-220
+    if (int r = use_device(c)) return r;
+    if (int r = upload_thresholds(c, thresholds, iterations)) return r;
+    LwsbStencil st;
+    if (int r = get_stencil(c, LWSB_W, fold_for(c->Q, flags), c->Q, 1, &st)) return r;
+    if (int r = begin_compute(c)) return r;
+    launch_sweeps_generic(c->view(), st, c->dthr.as<const double>(), iterations, c->stream);
+    c->launches += 1;
+    return end_compute(c);
+}
+
+extern "C" int lwsb_nofuture(lwsb_ctx *c, int which, const double *thresholds, int iterations, int flags)
+{
+    CHECK_CTX(c);
+    if (which < 0 || which > 2 || iterations < 0 || (iterations > 0 && !thresholds))
+        return fail(c, LWSB_ERR_ARG, "bad lwsb_nofuture arguments");
+    if (int r = check_resident(c)) return r;
+    if (iterations == 0) return LWSB_OK; // lws.pyx:272-273
+    if (!c->w[which].valid() || c->w[which].Q != c->Q || c->w[which].L != c->L)
+        return fail(c, LWSB_ERR_STATE, "no-future weight set missing or of a different shape than LWSB_W");
+    if (int r = use_device(c)) return r;
+    if (int r = upload_thresholds(c, thresholds, iterations)) return r;
+    const int fold = fold_for(c->Q, flags);
+    LwsbStencil st;
+    if (fold == LWSB_FOLD_Q4) { // NoFuture_LWSQ4, reproduced as written (lwslib.cpp:538-617)
+        if (int r = get_stencil(c, which, LWSB_FOLD_NF4, 1, 0, &st)) return r;
+        if (int r = begin_compute(c)) return r;
+        launch_nofuture_q4(c->view(), st, c->dthr.as<const double>(), iterations, c->stream);
+    } else {
+        if (int r = get_stencil(c, which, fold, 1, 0, &st)) return r;
+        if (int r = begin_compute(c)) return r;
+        launch_sweeps_generic(c->view(), st, c->dthr.as<const double>(), iterations, c->stream);
+    }
+    c->launches += 1;
+    return end_compute(c);
+}
+
+extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations, int look_ahead, int flags)
+{
+    CHECK_CTX(c);
+    if (iterations < 0 || (iterations > 0 && !thresholds) || look_ahead < 0)
+        return fail(c, LWSB_ERR_ARG, "bad lwsb_online arguments");
+    if (int r = check_resident(c)) return r;
+    if (iterations == 0) return LWSB_OK; // lws.pyx:332-333
+    for (int i = 1; i < 3; ++i)
+        if (!c->w[i].valid() || c->w[i].Q != c->Q || c->w[i].L != c->L)
+            return fail(c, LWSB_ERR_STATE, "online mode needs W, W_ai and W_af of the same shape");
+    if (c->Nreal > online_generic_max_nreal(c->L))
+        return fail(c, LWSB_ERR_UNSUPPORTED, "spectrum too wide for the online kernel");
+    if (int r = use_device(c)) return r;
+    if (int r = upload_thresholds(c, thresholds, iterations)) return r;
+    const int fold = fold_for(c->Q, flags), Q = c->Q;
+    // table: [rframe-1] for W with rframe 2..Q (index 0 unused), [Q] = W_ai init, [Q+1] = W_af
+    std::vector<LwsbStencil> sts(Q + 2, LwsbStencil{nullptr, nullptr, 0});
+    for (int rf = 2; rf <= Q; ++rf)
+        if (int r = get_stencil(c, LWSB_W, fold, rf, 1, &sts[rf - 1])) return r;
+    if (int r = get_stencil(c, LWSB_W_AI, fold, 1, 0, &sts[Q])) return r;
+    if (int r = get_stencil(c, LWSB_W_AF, fold, 1, 1, &sts[Q + 1])) return r;
+    CU(c, c->dsts.reserve(sts.size() * sizeof(LwsbStencil)));
+    CU(c, cudaMemcpyAsync(c->dsts.p, sts.data(), sts.size() * sizeof(LwsbStencil), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (int r = begin_compute(c)) return r;
+    launch_online_generic(c->view(), c->dsts.as<const LwsbStencil>(), c->dthr.as<const double>(), iterations,
+                          look_ahead, c->stream);
+    c->launches += 1;
+    return end_compute(c);
+}
+
+// Between two chained stages the reference crops and re-extends (lws.pyx:256 then 235-240 of the
+// next call): ghost frames become copies of the *updated* edge frames, |.| and its mean are
+// recomputed from the updated values.
+static int restage(lwsb_ctx *c)
+{
+    launch_reextend(c->view(), c->row_sum.as<double>(), c->row_max.as<double>(), c->mean_amp.as<double>(),
+                    c->max_amp.as<double>(), c->maxT + 2 * (c->Q - 1), c->stream);
+    c->launches += 3;
+    CU(c, cudaGetLastError());
+    return LWSB_OK;
+}
+
+// ============================================================================ one-shot interface
+extern "C" int lwsb_batch_lws(lwsb_ctx *c, const void *const *S_in, void *const *S_out, const int *T, int B, int Nreal,
+                              int kind, int where, const double *thresholds, int iterations, int flags)
+{
+    if (int r = lwsb_load(c, S_in, T, B, Nreal, kind, where)) return r;
+    if (int r = lwsb_batch(c, thresholds, iterations, flags)) return r;
+    return lwsb_store(c, S_out, where);
+}
+
+extern "C" int lwsb_nofuture_lws(lwsb_ctx *c, int which, const void *const *S_in, void *const *S_out, const int *T,
+                                 int B, int Nreal, int kind, int where, const double *thresholds, int iterations,
+                                 int flags)
+{
+    if (int r = lwsb_load(c, S_in, T, B, Nreal, kind, where)) return r;
+    if (int r = lwsb_nofuture(c, which, thresholds, iterations, flags)) return r;
+    return lwsb_store(c, S_out, where);
+}
+
+extern "C" int lwsb_online_lws(lwsb_ctx *c, const void *const *S_in, void *const *S_out, const int *T, int B, int Nreal,
+                               int kind, int where, const double *thresholds, int iterations, int look_ahead, int flags)
+{
+    if (int r = lwsb_load(c, S_in, T, B, Nreal, kind, where)) return r;
+    if (int r = lwsb_online(c, thresholds, iterations, look_ahead, flags)) return r;
+    return lwsb_store(c, S_out, where);
+}
+
+extern "C" int lwsb_run_lws(lwsb_ctx *c, const void *const *S_in, void *const *S_out, const int *T, int B, int Nreal,
+                            int kind, int where, const double *nofuture_thr, int nofuture_it, const double *online_thr,
+                            int online_it, int look_ahead, const double *batch_thr, int batch_it, int flags)
+{
+    if (int r = lwsb_load(c, S_in, T, B, Nreal, kind, where)) return r;
+    bool dirty = false;
+    if (nofuture_it > 0) {
+        if (int r = lwsb_nofuture(c, LWSB_W_AI, nofuture_thr, nofuture_it, flags)) return r;
+        dirty = true;
+    }
+    if (online_it > 0) {
+        if (dirty) if (int r = restage(c)) return r;
+        if (int r = lwsb_online(c, online_thr, online_it, look_ahead, flags)) return r;
+        dirty = true;
+    }
+    if (batch_it > 0) {
+        if (dirty) if (int r = restage(c)) return r;
+        if (int r = lwsb_batch(c, batch_thr, batch_it, flags)) return r;
+    }
+    return lwsb_store(c, S_out, where);
+}
+
+// ============================================================================ stft / istft
+extern "C" int lwsb_stft_frames(int nsamples, int fsize, int fshift, int perfectrec)
+{
+    // lws.pyx:54-77
+    if (nsamples < 0 || fsize < 1 || fshift < 1) return LWSB_ERR_ARG;
+    if (perfectrec) {
+        const int res = fsize % fshift;
+        const int pre = res == 0 ? fsize - fshift : fsize - res;
+        const int post = (fshift - nsamples % fshift) % fshift;
+        return (pre + nsamples + post) / fshift;
+    }
+    const int d = nsamples - fsize;
+    const int post = ((fshift - d % fshift) % fshift + fshift) % fshift;
+    return (nsamples + post - fsize) / fshift + 1;
+}
+
+extern "C" int lwsb_istft_length(int M, int fsize, int fshift, int perfectrec)
+{
+    // lws.pyx:116, 128-135
+    if (M < 1 || fsize < 1 || fshift < 1) return LWSB_ERR_ARG;
+    const int full = fshift * (M - 1) + fsize;
+    if (!perfectrec) return full;
+    const int res = fsize % fshift;
+    const int pre = res == 0 ? fsize - fshift : fsize - res;
+    const int n = full - pre - (fsize - fshift);
+    return n < 0 ? 0 : n;
+}
+
+extern "C" int lwsb_stft(lwsb_ctx *c, const double *x, int B, int nsamples, const double *awin, int fsize, int fshift,
+                         int fftsize, int perfectrec, void *S_out, int where)
+{
+    CHECK_CTX(c);
+    (void)x; (void)B; (void)nsamples; (void)awin; (void)fsize; (void)fshift; (void)fftsize; (void)perfectrec;
+    (void)S_out; (void)where;
+    return fail(c, LWSB_ERR_UNSUPPORTED, "lwsb_stft: not implemented yet");
+}
+
+extern "C" int lwsb_istft(lwsb_ctx *c, const void *S_in, int B, int M, int Nreal, const double *swin, int fshift,
+                          int perfectrec, double *x_out, int where)
+{
+    CHECK_CTX(c);
+    (void)S_in; (void)B; (void)M; (void)Nreal; (void)swin; (void)fshift; (void)perfectrec; (void)x_out; (void)where;
+    return fail(c, LWSB_ERR_UNSUPPORTED, "lwsb_istft: not implemented yet");
+}
+
+// ============================================================================ introspection
+extern "C" int lwsb_last_compute_ms(lwsb_ctx *c, float *ms)
+{
+    CHECK_CTX(c);
+    if (!ms) return fail(c, LWSB_ERR_ARG, "ms is NULL");
+    if (!c->timing_valid) return fail(c, LWSB_ERR_STATE, "no compute call timed yet");
+    if (int r = use_device(c)) return r;
+    CU(c, cudaEventSynchronize(c->ev1));
+    CU(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return LWSB_OK;
+}
+
+extern "C" long long lwsb_launch_count(const lwsb_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int lwsb_device_info(lwsb_ctx *c, int *sm_count, int *cc_major, int *cc_minor, long long *hbm_bytes)
+{
+    CHECK_CTX(c);
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (cc_major) *cc_major = c->prop.major;
+    if (cc_minor) *cc_minor = c->prop.minor;
+    if (hbm_bytes) *hbm_bytes = (long long)c->prop.totalGlobalMem;
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_get_stats(lwsb_ctx *c, double *mean_amp, double *max_amp)
+{
+    CHECK_CTX(c);
+    if (int r = check_resident(c)) return r;
+    if (int r = use_device(c)) return r;
+    if (mean_amp) CU(c, cudaMemcpyAsync(mean_amp, c->mean_amp.p, c->B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (max_amp) CU(c, cudaMemcpyAsync(max_amp, c->max_amp.p, c->B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LWSB_OK;
+}
+
+// ============================================================================ host-only debug mirrors
+extern "C" int lwsb_debug_terms(const double *wr, const double *wi, int Q, int L, int fold, int rframe, int cframe,
+                                int p, int max_terms, int *dr, int *dk, double *cr, double *ci)
+{
+    if (!wr || !wi || Q < 1 || L < 0 || p < 0 || p >= Q) return LWSB_ERR_ARG;
+    WeightSet w;
+    w.Q = Q; w.L = L;
+    const size_t n = (size_t)Q * Q * (L + 1);
+    w.wr.assign(wr, wr + n);
+    w.wi.assign(wi, wi + n);
+    std::vector<LwsbTerm> t;
+    build_terms(w, fold, rframe, cframe, p, t);
+    const int cnt = (int)t.size();
+    for (int i = 0; i < cnt && i < max_terms; ++i) {
+        if (dr) dr[i] = t[i].dr;
+        if (dk) dk[i] = t[i].dk;
+        if (cr) cr[i] = t[i].cr;
+        if (ci) ci[i] = t[i].ci;
+    }
+    return cnt;
+}
+
+extern "C" long long lwsb_debug_online_chain_length(int T, int iterations, int look_ahead)
+{
+    return lwsb_online_chain_len(T, iterations, look_ahead);
+}
+
+extern "C" int lwsb_debug_online_task(int T, int iterations, int look_ahead, int Q, long long j, int *row, int *which,
+                                      int *rframe, int *cframe, int *thr_index)
+{
+    if (j < 0 || j >= lwsb_online_chain_len(T, iterations, look_ahead)) return LWSB_ERR_ARG;
+    const LwsbOnlineTask t = lwsb_online_decode(T, iterations, look_ahead, Q, j);
+    if (row) *row = t.row;
+    if (which) *which = t.which;
+    if (rframe) *rframe = t.rframe;
+    if (cframe) *cframe = t.cframe;
+    if (thr_index) *thr_index = t.thr;
+    return LWSB_OK;
+}

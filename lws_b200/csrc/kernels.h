@@ -1,0 +1,21 @@
+// kernels.h -- launch wrappers implemented in the .cu files (host-callable).
+#pragma once
+#include <cuda_runtime.h>
+#include "lwsb_common.h"
+
+namespace lwsb {
+
+// kernels_generic.cu
+void launch_extend(const LwsbView &v, int kind, const void *const *src, double *row_sum, double *row_max,
+                   double *mean_amp, double *max_amp, int maxTp, cudaStream_t s);
+void launch_refresh_ghosts(const LwsbView &v, cudaStream_t s);
+void launch_reextend(const LwsbView &v, double *row_sum, double *row_max, double *mean_amp, double *max_amp,
+                     int maxTp, cudaStream_t s);
+void launch_crop(const LwsbView &v, void *const *dst, int maxT, cudaStream_t s);
+void launch_sweeps_generic(const LwsbView &v, const LwsbStencil &st, const double *thr, int iters, cudaStream_t s);
+void launch_online_generic(const LwsbView &v, const LwsbStencil *sts, const double *thr, int iters, int LA,
+                           cudaStream_t s);
+void launch_nofuture_q4(const LwsbView &v, const LwsbStencil &st, const double *thr, int iters, cudaStream_t s);
+inline int online_generic_max_nreal(int L) { return (1024 - 1) * (L + 1); }
+
+} // namespace lwsb
