@@ -105,14 +105,22 @@ int lwsb_run_lws(lwsb_ctx *ctx, const void *const *S_in, void *const *S_out, con
                  int online_it, int look_ahead, const double *batch_thr, int batch_it, int flags);
 
 /* ---- stft / istft (lws.pyx:43-90, 93-137), batched over signals of equal length ---------
- * x: (B, nsamples) real; S: (B, M, fftsize/2+1) complex128.  perfectrec padding as the
- * reference; M and the output length are returned by the *_shape helpers. */
+ * lwsb_stft : x (B, nsamples) real -> S (B, M, fftsize/2+1) complex128.  Frame m covers the
+ *             padded samples [m*fshift, m*fshift + fsize) where padded sample p is x[p - pre_pad]
+ *             (zero outside the signal): pre_pad and M are what lws.pyx:54-77 derive from
+ *             `perfectrec` (lwsb_stft_frames / lwsb_stft_prepad compute them).  The frame is
+ *             multiplied by awin[fsize] and transformed with an fftsize-point DFT (zero-padded
+ *             or cropped like np.fft.fft(frame, n=fftsize), lws.pyx:85-88).
+ * lwsb_istft: S (B, M, Nreal) -> overlap-added signal (B, fshift*(M-1) + 2*(Nreal-1)), every
+ *             inverse frame multiplied by swin (zero beyond nswin), lws.pyx:116-126.  The
+ *             perfect-reconstruction crop of lws.pyx:128-135 is a slice the caller takes.
+ * awin / swin are host pointers; x / S live where `where` says. */
 int lwsb_stft_frames(int nsamples, int fsize, int fshift, int perfectrec);
-int lwsb_istft_length(int M, int fsize, int fshift, int perfectrec);
+int lwsb_stft_prepad(int fsize, int fshift, int perfectrec);
 int lwsb_stft(lwsb_ctx *ctx, const double *x, int B, int nsamples, const double *awin, int fsize, int fshift,
-              int fftsize, int perfectrec, void *S_out, int where);
-int lwsb_istft(lwsb_ctx *ctx, const void *S_in, int B, int M, int Nreal, const double *swin, int fshift,
-               int perfectrec, double *x_out, int where);
+              int fftsize, int pre_pad, int M, void *S_out, int where);
+int lwsb_istft(lwsb_ctx *ctx, const void *S_in, int B, int M, int Nreal, const double *swin, int nswin, int fshift,
+               double *x_out, int where);
 
 /* ---- introspection used by bench.py / tests -------------------------------------------- */
 /* device time (ms, CUDA events on the context's stream) of the compute kernels of the last

@@ -42,8 +42,8 @@ SIGNATURES = {
     "lwsb_online_lws": (_ci, [_vp, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _ci, _ci]),
     "lwsb_run_lws": (_ci, [_vp, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _dp, _ci, _ci, _dp, _ci, _ci]),
     "lwsb_stft_frames": (_ci, [_ci, _ci, _ci, _ci]),
-    "lwsb_istft_length": (_ci, [_ci, _ci, _ci, _ci]),
-    "lwsb_stft": (_ci, [_vp, _vp, _ci, _ci, _dp, _ci, _ci, _ci, _ci, _vp, _ci]),
+        "lwsb_stft_prepad": (_ci, [_ci, _ci, _ci]),
+    "lwsb_stft": (_ci, [_vp, _vp, _ci, _ci, _dp, _ci, _ci, _ci, _ci, _ci, _vp, _ci]),
     "lwsb_istft": (_ci, [_vp, _vp, _ci, _ci, _ci, _dp, _ci, _ci, _vp, _ci]),
     "lwsb_last_compute_ms": (_ci, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "lwsb_launch_count": (_ll, [_vp]),
@@ -223,6 +223,27 @@ class Context(object):
         self._c(lib().lwsb_run_lws(self._h, _ptr_array(arrays), _ptr_array(outs), T.ctypes.data_as(_ip), len(arrays),
                                    arrays[0].shape[1], kind, HOST, p1, n1, p2, n2, int(look_ahead), p3, n3, flags))
         return outs
+
+    # -- transforms -------------------------------------------------------------------------
+    def stft(self, x, awin, fsize, fshift, fftsize, perfectrec):
+        """x: (B, nsamples) float64 C-contiguous -> (B, M, fftsize//2+1) complex128."""
+        B, n = x.shape
+        M = _check(lib().lwsb_stft_frames(n, fsize, fshift, int(bool(perfectrec))))
+        pre = _check(lib().lwsb_stft_prepad(fsize, fshift, int(bool(perfectrec))))
+        S = np.empty((B, M, fftsize // 2 + 1), dtype=np.complex128)
+        awin = np.ascontiguousarray(awin, dtype=np.float64)
+        self._c(lib().lwsb_stft(self._h, x.ctypes.data, B, n, _dptr(awin), fsize, fshift, fftsize, pre, M,
+                                S.ctypes.data, HOST))
+        return S
+
+    def istft(self, S, swin, fshift):
+        """S: (B, M, Nreal) complex128 C-contiguous -> (B, fshift*(M-1) + 2*(Nreal-1)) float64 (uncropped)."""
+        B, M, Nreal = S.shape
+        swin = np.ascontiguousarray(swin, dtype=np.float64)
+        out = np.empty((B, fshift * (M - 1) + 2 * (Nreal - 1)))
+        self._c(lib().lwsb_istft(self._h, S.ctypes.data, B, M, Nreal, _dptr(swin), len(swin), fshift,
+                                 out.ctypes.data, HOST))
+        return out
 
     # -- introspection ----------------------------------------------------------------------
     def last_compute_ms(self):

@@ -57,7 +57,9 @@ def _as_batch(S):
     return arrs, (_native.C128 if cplx else _native.F64), shape
 
 
-def _rebuild(outs, shape):
+def _rebuild(outs, shape, out=None):
+    if out is not None:
+        return out
     if shape == "2d":
         return outs[0]
     if shape == "3d":
@@ -70,7 +72,16 @@ def _is_views_of_one(outs):
     return b is not None and b.ndim == 3 and all(o.base is b for o in outs)
 
 
-def _alloc_outs(arrs, shape):
+def _alloc_outs(arrs, shape, out=None):
+    if out is not None:
+        # caller-provided result buffer(s) (e.g. pinned host memory): complex128, C-contiguous
+        outs = list(out) if isinstance(out, (list, tuple)) else ([out[b] for b in range(len(arrs))] if shape == "3d" else [out])
+        for a, o in zip(arrs, outs):
+            if o.shape != a.shape or o.dtype != np.complex128 or not o.flags.c_contiguous:
+                raise ValueError('out= must be C-contiguous complex128 of the input shape')
+        if len(outs) != len(arrs):
+            raise ValueError('out= does not match the batch')
+        return outs
     if shape == "3d":
         big = np.empty((len(arrs),) + arrs[0].shape, dtype=np.complex128)
         return [big[b] for b in range(len(arrs))]
@@ -131,48 +142,48 @@ def _run_sharded(devices, arrs, outs, fn):
         raise errs[0]
 
 
-def batch_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=0):
+def batch_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=0, out=None):
     """Batch-mode LWS phase reconstruction (lws.pyx:209-258)."""
     if len(thresholds) == 0:
         return _passthrough(S)
     arrs, kind, shape = _as_batch(S)
     _check_shapes(arrs)
     _check_weights(W, use_simplifications)
-    outs = _alloc_outs(arrs, shape)
+    outs = _alloc_outs(arrs, shape, out)
 
     def fn(ctx, a, o):
         ctx.set_weights(_native.W, W)
         ctx.batch_lws(a, kind, thresholds, flags, outs=o)
 
     _run_sharded(_devices(device), arrs, outs, fn)
-    return _rebuild(outs, shape)
+    return _rebuild(outs, shape, out)
 
 
-def nofuture_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=0):
+def nofuture_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=0, out=None):
     """LWS using past frames only, typically for initialisation (lws.pyx:261-311)."""
     if len(thresholds) == 0:
         return _passthrough(S)
     arrs, kind, shape = _as_batch(S)
     _check_shapes(arrs)
     _check_weights(W, use_simplifications)
-    outs = _alloc_outs(arrs, shape)
+    outs = _alloc_outs(arrs, shape, out)
 
     def fn(ctx, a, o):
         ctx.set_weights(_native.W, W)
         ctx.nofuture_lws(_native.W, a, kind, thresholds, flags, outs=o)
 
     _run_sharded(_devices(device), arrs, outs, fn)
-    return _rebuild(outs, shape)
+    return _rebuild(outs, shape, out)
 
 
-def online_lws(S, W, W_ai, W_af, thresholds, LA, fshift, use_simplifications=True, *, device=None, flags=0):
+def online_lws(S, W, W_ai, W_af, thresholds, LA, fshift, use_simplifications=True, *, device=None, flags=0, out=None):
     """Online (TF-RTISI-LA) LWS phase reconstruction (lws.pyx:314-375)."""
     if len(thresholds) == 0:
         return _passthrough(S)
     arrs, kind, shape = _as_batch(S)
     _check_shapes(arrs)
     _check_weights(W, use_simplifications)
-    outs = _alloc_outs(arrs, shape)
+    outs = _alloc_outs(arrs, shape, out)
 
     def fn(ctx, a, o):
         ctx.set_weights(_native.W, W)
@@ -181,7 +192,7 @@ def online_lws(S, W, W_ai, W_af, thresholds, LA, fshift, use_simplifications=Tru
         ctx.online_lws(a, kind, thresholds, int(LA), flags, outs=o)
 
     _run_sharded(_devices(device), arrs, outs, fn)
-    return _rebuild(outs, shape)
+    return _rebuild(outs, shape, out)
 
 
 class lws(object):
@@ -285,29 +296,30 @@ class lws(object):
         return transforms.istft(S, self.fshift, self.swin, perfectrec=self.perfectrec, device=self.device)
 
     # ---- phase reconstruction (GPU) -----------------------------------------------------------
-    def nofuture_lws(self, S, iterations=None, thresholds=None):
+    def nofuture_lws(self, S, iterations=None, thresholds=None, *, out=None):
         if iterations is None:
             iterations = self.nofuture_iterations
         if thresholds is None:
             thresholds = get_thresholds(iterations, self.nofuture_alpha, self.nofuture_beta, self.nofuture_gamma)
-        return nofuture_lws(S, self.W_ai, thresholds, use_simplifications=self.use_simplifications, device=self.device)
+        return nofuture_lws(S, self.W_ai, thresholds, use_simplifications=self.use_simplifications, device=self.device,
+                            out=out)
 
-    def online_lws(self, S, iterations=None, thresholds=None):
+    def online_lws(self, S, iterations=None, thresholds=None, *, out=None):
         if iterations is None:
             iterations = self.online_iterations
         if thresholds is None:
             thresholds = get_thresholds(iterations, self.online_alpha, self.online_beta, self.online_gamma)
         return online_lws(S, self.W, self.W_ai, self.W_af, thresholds, self.look_ahead, self.fshift,
-                          use_simplifications=self.use_simplifications, device=self.device)
+                          use_simplifications=self.use_simplifications, device=self.device, out=out)
 
-    def batch_lws(self, S, iterations=None, thresholds=None):
+    def batch_lws(self, S, iterations=None, thresholds=None, *, out=None):
         if iterations is None:
             iterations = self.batch_iterations
         if thresholds is None:
             thresholds = get_thresholds(iterations, self.batch_alpha, self.batch_beta, self.batch_gamma)
-        return batch_lws(S, self.W, thresholds, use_simplifications=self.use_simplifications, device=self.device)
+        return batch_lws(S, self.W, thresholds, use_simplifications=self.use_simplifications, device=self.device, out=out)
 
-    def run_lws(self, S):
+    def run_lws(self, S, *, out=None):
         """nofuture -> online -> batch (lws.pyx:495-499), fused on the device: the spectrograms
         cross PCIe once in each direction instead of three times."""
         nf = get_thresholds(self.nofuture_iterations, self.nofuture_alpha, self.nofuture_beta, self.nofuture_gamma)
@@ -318,7 +330,7 @@ class lws(object):
         arrs, kind, shape = _as_batch(S)
         _check_shapes(arrs)
         _check_weights(self.W, self.use_simplifications)
-        outs = _alloc_outs(arrs, shape)
+        outs = _alloc_outs(arrs, shape, out)
 
         def fn(ctx, a, o):
             ctx.set_weights(_native.W, self.W)
@@ -327,4 +339,4 @@ class lws(object):
             ctx.run_lws(a, kind, nf, on, self.look_ahead, ba, outs=o)
 
         _run_sharded(_devices(self.device), arrs, outs, fn)
-        return _rebuild(outs, shape)
+        return _rebuild(outs, shape, out)

@@ -63,6 +63,8 @@ struct lwsb_ctx {
     std::vector<int> T;
     std::vector<long long> rowbase, binbase;
     DevBuf E, A, row_sum, row_max, mean_amp, max_amp, dT, drowbase, stage, dptr, dthr, dsts, flags;
+    DevBuf fx, fS, fwin, fframes;          // stft / istft staging
+    std::map<int, DevBuf> twiddles;        // exp(-2 pi i j / N) tables by N
     std::vector<void *> hptr;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -216,8 +218,9 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 3; ++i) drop_stencils(c, i);
     for (DevBuf *b : {&c->E, &c->A, &c->row_sum, &c->row_max, &c->mean_amp, &c->max_amp, &c->dT, &c->drowbase,
-                      &c->stage, &c->dptr, &c->dthr, &c->dsts, &c->flags})
+                      &c->stage, &c->dptr, &c->dthr, &c->dsts, &c->flags, &c->fx, &c->fS, &c->fwin, &c->fframes})
         b->release();
+    for (auto &kv : c->twiddles) kv.second.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -536,33 +539,119 @@ extern "C" int lwsb_stft_frames(int nsamples, int fsize, int fshift, int perfect
     return (nsamples + post - fsize) / fshift + 1;
 }
 
-extern "C" int lwsb_istft_length(int M, int fsize, int fshift, int perfectrec)
+extern "C" int lwsb_stft_prepad(int fsize, int fshift, int perfectrec)
 {
-    // lws.pyx:116, 128-135
-    if (M < 1 || fsize < 1 || fshift < 1) return LWSB_ERR_ARG;
-    const int full = fshift * (M - 1) + fsize;
-    if (!perfectrec) return full;
+    // lws.pyx:54-60
+    if (fsize < 1 || fshift < 1) return LWSB_ERR_ARG;
+    if (!perfectrec) return 0;
     const int res = fsize % fshift;
-    const int pre = res == 0 ? fsize - fshift : fsize - res;
-    const int n = full - pre - (fsize - fshift);
-    return n < 0 ? 0 : n;
+    return res == 0 ? fsize - fshift : fsize - res;
 }
+
+namespace {
+
+// exp(-2*pi*i*j/N), j in [0, N): host-computed once per N in fp64, the axis points set exactly
+int get_twiddles(lwsb_ctx *c, int N, const double2 **out)
+{
+    auto it = c->twiddles.find(N);
+    if (it == c->twiddles.end()) {
+        std::vector<double2> h(N);
+        for (int j = 0; j < N; ++j) {
+            const double a = -2.0 * M_PI * (double)j / (double)N;
+            h[j] = make_double2(std::cos(a), std::sin(a));
+        }
+        if (N % 4 == 0) { h[N / 4] = make_double2(0.0, -1.0); h[3 * N / 4] = make_double2(0.0, 1.0); }
+        if (N % 2 == 0) h[N / 2] = make_double2(-1.0, 0.0);
+        DevBuf b;
+        CU(c, b.reserve((size_t)N * sizeof(double2)));
+        CU(c, cudaMemcpyAsync(b.p, h.data(), (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        it = c->twiddles.emplace(N, b).first;
+    }
+    *out = it->second.as<const double2>();
+    return LWSB_OK;
+}
+
+int ilog2_exact(int N)
+{
+    int l = 0;
+    while ((1 << l) < N) ++l;
+    return (1 << l) == N ? l : -1;
+}
+
+} // namespace
 
 extern "C" int lwsb_stft(lwsb_ctx *c, const double *x, int B, int nsamples, const double *awin, int fsize, int fshift,
-                         int fftsize, int perfectrec, void *S_out, int where)
+                         int fftsize, int pre_pad, int M, void *S_out, int where)
 {
     CHECK_CTX(c);
-    (void)x; (void)B; (void)nsamples; (void)awin; (void)fsize; (void)fshift; (void)fftsize; (void)perfectrec;
-    (void)S_out; (void)where;
-    return fail(c, LWSB_ERR_UNSUPPORTED, "lwsb_stft: not implemented yet");
+    if (!x || !awin || !S_out || B < 1 || nsamples < 0 || fsize < 1 || fshift < 1 || fftsize < 2 || pre_pad < 0 || M < 1 ||
+        (where != LWSB_HOST && where != LWSB_DEVICE))
+        return fail(c, LWSB_ERR_ARG, "bad lwsb_stft arguments");
+    if (fftsize % 2 == 1) return fail(c, LWSB_ERR_ARG, "Odd ffts not supported."); // lws.pyx:51-52
+    if (int r = use_device(c)) return r;
+    const int N = fftsize, Nb = N / 2 + 1;
+    int logN = ilog2_exact(N);
+    if (logN >= 0 && (size_t)N * sizeof(double2) > c->prop.sharedMemPerBlockOptin) logN = -1;
+    if (logN < 0 && (size_t)N * sizeof(double) > c->prop.sharedMemPerBlockOptin)
+        return fail(c, LWSB_ERR_UNSUPPORTED, "fftsize too large for the on-chip transform");
+    const double2 *tw;
+    if (int r = get_twiddles(c, N, &tw)) return r;
+    const size_t nx = (size_t)B * std::max(nsamples, 1), nS = (size_t)B * M * Nb;
+    CU(c, c->fwin.reserve((size_t)fsize * sizeof(double)));
+    CU(c, cudaMemcpyAsync(c->fwin.p, awin, (size_t)fsize * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const double *dx = x;
+    double2 *dS = reinterpret_cast<double2 *>(S_out);
+    if (where == LWSB_HOST) {
+        CU(c, c->fx.reserve(nx * sizeof(double)));
+        CU(c, c->fS.reserve(nS * sizeof(double2)));
+        if (nsamples > 0)
+            CU(c, cudaMemcpyAsync(c->fx.p, x, (size_t)B * nsamples * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        dx = c->fx.as<double>();
+        dS = c->fS.as<double2>();
+    }
+    CU(c, launch_stft(dx, B, nsamples, c->fwin.as<double>(), fsize, fshift, N, logN, pre_pad, tw, dS, M, c->stream));
+    c->launches += 1;
+    if (where == LWSB_HOST) CU(c, cudaMemcpyAsync(S_out, dS, nS * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LWSB_OK;
 }
 
-extern "C" int lwsb_istft(lwsb_ctx *c, const void *S_in, int B, int M, int Nreal, const double *swin, int fshift,
-                          int perfectrec, double *x_out, int where)
+extern "C" int lwsb_istft(lwsb_ctx *c, const void *S_in, int B, int M, int Nreal, const double *swin, int nswin,
+                          int fshift, double *x_out, int where)
 {
     CHECK_CTX(c);
-    (void)S_in; (void)B; (void)M; (void)Nreal; (void)swin; (void)fshift; (void)perfectrec; (void)x_out; (void)where;
-    return fail(c, LWSB_ERR_UNSUPPORTED, "lwsb_istft: not implemented yet");
+    if (!S_in || !swin || !x_out || B < 1 || M < 1 || Nreal < 2 || nswin < 1 || fshift < 1 ||
+        (where != LWSB_HOST && where != LWSB_DEVICE))
+        return fail(c, LWSB_ERR_ARG, "bad lwsb_istft arguments");
+    if (Nreal % 2 != 1) // lws.pyx:100-101
+        return fail(c, LWSB_ERR_EVEN_NREAL, "We expect the spectrogram to only have non-negative frequencies");
+    if (int r = use_device(c)) return r;
+    const int N = 2 * (Nreal - 1);
+    int logN = ilog2_exact(N);
+    if (logN >= 0 && (size_t)N * sizeof(double2) > c->prop.sharedMemPerBlockOptin) logN = -1;
+    if (logN < 0 && (size_t)(N / 2 + 2) * sizeof(double2) > c->prop.sharedMemPerBlockOptin)
+        return fail(c, LWSB_ERR_UNSUPPORTED, "spectrum too wide for the on-chip transform");
+    const double2 *tw;
+    if (int r = get_twiddles(c, N, &tw)) return r;
+    const size_t len = (size_t)fshift * (M - 1) + N, nS = (size_t)B * M * Nreal;
+    CU(c, c->fwin.reserve((size_t)nswin * sizeof(double)));
+    CU(c, cudaMemcpyAsync(c->fwin.p, swin, (size_t)nswin * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, c->fframes.reserve((size_t)B * M * N * sizeof(double)));
+    const double2 *dS = reinterpret_cast<const double2 *>(S_in);
+    double *dx = x_out;
+    if (where == LWSB_HOST) {
+        CU(c, c->fS.reserve(nS * sizeof(double2)));
+        CU(c, c->fx.reserve((size_t)B * len * sizeof(double)));
+        CU(c, cudaMemcpyAsync(c->fS.p, S_in, nS * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+        dS = c->fS.as<const double2>();
+        dx = c->fx.as<double>();
+    }
+    CU(c, launch_istft(dS, B, M, N, logN, c->fwin.as<double>(), nswin, fshift, tw, c->fframes.as<double>(), dx, c->stream));
+    c->launches += 2;
+    if (where == LWSB_HOST) CU(c, cudaMemcpyAsync(x_out, dx, (size_t)B * len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LWSB_OK;
 }
 
 // ============================================================================ introspection

@@ -16,6 +16,12 @@ void launch_sweeps_generic(const LwsbView &v, const LwsbStencil &st, const doubl
 void launch_online_generic(const LwsbView &v, const LwsbStencil *sts, const double *thr, int iters, int LA,
                            cudaStream_t s);
 void launch_nofuture_q4(const LwsbView &v, const LwsbStencil &st, const double *thr, int iters, cudaStream_t s);
+
+// kernels_fft.cu
+cudaError_t launch_stft(const double *x, int B, int nsamples, const double *awin, int fsize, int hop, int N, int logN,
+                        int pre, const double2 *tw, double2 *S, int M, cudaStream_t s);
+cudaError_t launch_istft(const double2 *S, int B, int M, int N, int logN, const double *swin, int nswin, int hop,
+                         const double2 *tw, double *frames, double *signal, cudaStream_t s);
 inline int online_generic_max_nreal(int L) { return (1024 - 1) * (L + 1); }
 
 } // namespace lwsb

@@ -1,0 +1,225 @@
+"""CPU-side checks of the product's host logic and C-ABI (no GPU, no compute calls):
+
+* liblws_b200.so loads and exports every symbol include/lws_b200.h declares;
+* create_weights (host C++) and the window helpers against the golden vectors;
+* the stencil tables + the wavefront / pipelined-sweep / online-chain schedules the kernels
+  execute, replayed in numpy with *concurrent-step semantics* (all bins of a step read the
+  state as it was when the step began), must reproduce the sequential oracle exactly;
+* reference API behaviours that are decided before any kernel runs.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SMALL_CASES, golden, relF
+
+import lws_b200
+from lws_b200 import _native, dsp
+
+NAMES = [c["name"] for c in SMALL_CASES]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "lws_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(lwsb_\w+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = ctypes.CDLL(_native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "missing export: " + name
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert _native.lib().lwsb_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        _native.Context(0)
+    with pytest.raises(RuntimeError):
+        lws_b200.lws(32, 8).batch_lws(np.ones((5, 17)), iterations=1)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "lws_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "lws_oracle" not in src and "oracle/" not in src, f
+
+
+@pytest.mark.parametrize("case", SMALL_CASES, ids=NAMES)
+def test_windows_and_weights_match_golden(case, capsys):
+    g = golden(case["name"])
+    kw = dict(case["kwargs"])
+    if case["name"] == "custom_win":
+        p = lws_b200.lws(g["awin_in"], case["args"][1], swin=g["swin_in"], mode="music", **kw)
+    else:
+        p = lws_b200.lws(*case["args"], mode="music", **kw)
+    assert np.array_equal(p.awin, g["awin"]) and np.array_equal(p.swin, g["swin"])
+    if "win_ai" in g:
+        assert np.array_equal(p.win_ai, g["win_ai"]) and np.array_equal(p.win_af, g["win_af"])
+    for k in ("W", "W_ai", "W_af"):
+        assert getattr(p, k).shape == g[k].shape
+        assert np.abs(getattr(p, k) - g[k]).max() < 1e-14, k
+    assert p.nofuture_iterations == 1 and p.online_iterations == 10 and p.batch_iterations == 100
+
+
+def test_stft_geometry_matches_oracle(oracle):
+    lib = _native.lib()
+    for fs, hop in ((32, 8), (64, 16), (48, 8), (36, 12), (50, 20), (512, 128)):
+        awin = np.ones(fs)
+        for n in (1, hop - 1, hop, fs, fs + 1, 1000, 1001, 4096):
+            for pr in (True, False):
+                if not pr and n < fs:
+                    continue
+                M = oracle.stft(np.zeros(n), fs, hop, awin, perfectrec=pr).shape[0]
+                assert lib.lwsb_stft_frames(n, fs, hop, int(pr)) == M, (fs, hop, n, pr)
+
+
+def test_api_checks_before_any_kernel():
+    p = lws_b200.lws(32, 8)
+    Sc = np.ones((6, 17), dtype=np.complex128)
+    assert p.batch_lws(Sc, iterations=0) is Sc
+    assert p.online_lws(Sc) is Sc and p.nofuture_lws(Sc) is Sc  # default mode: 0 iterations
+    out = p.batch_lws(np.ones((6, 17), dtype=np.float32), iterations=0)
+    assert out.dtype == np.complex128
+    with pytest.raises(ValueError, match="non-negative frequencies"):
+        p.batch_lws(np.ones((6, 16)), iterations=1)
+    with pytest.raises(ValueError):
+        lws_b200.stft(np.ones((2, 2, 2)), 4, 2, np.ones(4))
+    with pytest.raises(ValueError, match="Odd ffts"):
+        lws_b200.stft(np.ones(20), 5, 2, np.ones(5))
+    with pytest.raises(ValueError):
+        lws_b200.lws(32, 8, fftsize=35)
+    with pytest.raises(TypeError):
+        lws_b200.lws(np.ones((2, 32)), 8)
+    assert np.array_equal(lws_b200.get_thresholds(4, 100, 0.1, 1), 100 * np.exp(-0.1 * np.arange(4)))
+
+
+# ------------------------------------------------------------------ schedule replays
+FOLD = {2: 2, 4: 4}
+
+
+def _tables(W, fold, rframe, cframe):
+    Q = W.shape[1]
+    return [_native.debug_terms(W, fold, rframe, cframe, p) for p in range(Q)]
+
+
+def _update(E, A, row, c, L, Nreal, terms, thr, src=None):
+    """one bin, the kernels' update_bin/commit_bin; reads from `src` (step snapshot)"""
+    src = E if src is None else src
+    a = A[row, c + L]
+    if not (a > thr):
+        return
+    dr, dk, co = terms[c % len(terms)]
+    t = np.sum(co * src[row + dr, c + L + dk])
+    mag = abs(t)
+    if mag > 0:
+        v = t * a / mag
+        E[row, c + L] = v
+        if 1 <= c <= L:
+            E[row, L - c] = np.conj(v)
+        elif Nreal - 1 - L <= c <= Nreal - 2:
+            E[row, L + 2 * (Nreal - 1) - c] = np.conj(v)
+
+
+@pytest.mark.parametrize("name", ["q2", "q4", "q8b", "q3", "q4_L3"])
+def test_pipelined_wavefront_equals_sequential_sweeps(oracle, name):
+    """k_sweeps_generic's order: sweep i, frame m, bin c at step c + (L+1)*(m + Q*i)."""
+    case = [c for c in SMALL_CASES if c["name"] == name][0]
+    p = lws_b200.lws(*case["args"], **case["kwargs"])
+    po = oracle.lws(*case["args"], **case["kwargs"])
+    Q, L = p.W.shape[1], p.W.shape[2] - 1
+    A0 = np.abs(golden(name)["X"])[:14]
+    T, Nreal = A0.shape
+    thr = np.array([0.9, 0.0, 0.3, 0.0])
+    mean = np.mean(A0)
+    E = dsp.extspec(A0.astype(np.complex128), L, Q)
+    A = np.abs(E)
+    terms = _tables(p.W, FOLD.get(Q, 0), Q, 1)
+    S, iters = L + 1, len(thr)
+    tmax = S * ((T - 1) + Q * (iters - 1)) + Nreal - 1
+    for t in range(tmax + 1):
+        snap = E.copy()
+        for i in range(iters):
+            for m in range(T):
+                c = t - S * (m + Q * i)
+                if 0 <= c < Nreal:
+                    _update(E, A, m + Q - 1, c, L, Nreal, terms, thr[i] * mean, src=snap)
+    got = E[Q - 1:Q - 1 + T, L:L + Nreal]
+    want = po.batch_lws(A0, thresholds=thr)
+    assert relF(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("name,LA", [("q4", 3), ("q2_la4", 4), ("q8_la2", 2), ("q4_la0", 0)])
+def test_online_chain_equals_reference_schedule(oracle, name, LA):
+    """k_online_generic's order: row update j of the TF-RTISI-LA chain, bin c at step c + (L+1)*j."""
+    case = [c for c in SMALL_CASES if c["name"] == name][0]
+    p = lws_b200.lws(*case["args"], **case["kwargs"])
+    po = oracle.lws(*case["args"], **case["kwargs"])
+    assert p.look_ahead == LA
+    Q, L = p.W.shape[1], p.W.shape[2] - 1
+    A0 = np.abs(golden(name)["X"])[:9]
+    T, Nreal = A0.shape
+    iters = 2
+    thr = lws_b200.get_thresholds(iters, 1, 0.1, 1)
+    mean = np.mean(A0)
+    E = dsp.extspec(A0.astype(np.complex128), L, Q)
+    A = np.abs(E)
+    fold = FOLD.get(Q, 0)
+    tabs = {("W", rf): _tables(p.W, fold, rf, 1) for rf in range(2, Q + 1)}
+    tabs["ai"] = _tables(p.W_ai, fold, 1, 0)
+    tabs["af"] = _tables(p.W_af, fold, 1, 1)
+    chain = _native.debug_online_chain(T, iters, LA, Q)
+    assert len(chain) == sum(1 + iters * (min(LA, m) + 1) for m in range(T))
+    S = L + 1
+    for t in range(S * (len(chain) - 1) + Nreal):
+        snap = E.copy()
+        for j in range(max(0, (t - Nreal) // S), min(len(chain) - 1, t // S) + 1):
+            c = t - S * j
+            if not (0 <= c < Nreal):
+                continue
+            row, which, rframe, cframe, ti = chain[j]
+            terms = tabs[("W", rframe)] if which == 0 else (tabs["ai"] if which == 1 else tabs["af"])
+            _update(E, A, row, c, L, Nreal, terms, 0.0 if ti < 0 else thr[ti] * mean, src=snap)
+    got = E[Q - 1:Q - 1 + T, L:L + Nreal]
+    want = po.online_lws(A0, thresholds=thr)
+    assert relF(got, want) < 1e-12
+
+
+def test_nofuture_q4_table_reproduces_reference_indexing(oracle):
+    """LWSB_FOLD_NF4 terms applied with the reference's flat offset (m+dr)*Np + 2e + dk, raster order."""
+    p, po = lws_b200.lws(32, 8), oracle.lws(32, 8)
+    Q, L = 4, 5
+    A0 = np.abs(golden("q4")["X"])[:10]
+    T, Nreal = A0.shape
+    Np = Nreal + 2 * L
+    E = dsp.extspec(A0.astype(np.complex128), L, Q)
+    A = np.abs(E)
+    terms = _tables(p.W_ai, 5, 1, 0)
+    thr = 0.2 * np.mean(A0)
+    flat = E.reshape(-1)
+    for m in range(Q - 1, T + Q - 1):
+        for c in range(Nreal):
+            a = A[m, c + L]
+            if not (a > thr):
+                continue
+            dr, dk, co = terms[c % Q]
+            t = np.sum(co * flat[(m + dr) * Np + 2 * (c + L) + dk])
+            if abs(t) > 0:
+                v = t * a / abs(t)
+                E[m, c + L] = v
+                if 1 <= c <= L:
+                    E[m, L - c] = np.conj(v)
+                elif Nreal - 1 - L <= c <= Nreal - 2:
+                    E[m, L + 2 * (Nreal - 1) - c] = np.conj(v)
+    want = po.nofuture_lws(A0, thresholds=np.array([0.2]))
+    assert relF(E[Q - 1:Q - 1 + T, L:L + Nreal], want) < 1e-12
