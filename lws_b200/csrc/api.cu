@@ -39,12 +39,6 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-struct StencilDev {
-    DevBuf terms, count;
-    int maxt = 0;
-    LwsbStencil view() const { return LwsbStencil{terms.as<const LwsbTerm>(), count.as<const int>(), maxt}; }
-};
-
 } // namespace
 
 struct lwsb_ctx {
@@ -55,14 +49,15 @@ struct lwsb_ctx {
     cudaDeviceProp prop{};
 
     WeightSet w[3];
-    std::map<std::tuple<int, int, int, int>, StencilDev> stencils; // (which, fold, rframe, cframe)
+    DevBuf raww[3]; // device copy of wr | wi (2 * Q*Q*(L+1) doubles) followed by the int mask, reference layout
 
     // resident batch
     int B = 0, Nreal = 0, Q = 0, L = 0, P = 0, c0 = 0, maxT = 0;
     long long total_rows = 0, total_bins = 0;
     std::vector<int> T;
     std::vector<long long> rowbase, binbase;
-    DevBuf E, A, row_sum, row_max, mean_amp, max_amp, dT, drowbase, stage, dptr, dthr, dsts, flags;
+    DevBuf E, A, row_max, leaf_tab, leaf_sum, mean_amp, max_amp, dT, drowbase, stage, dptr, dthr, flags;
+    long long leaf_stride = 0;
     DevBuf fx, fS, fwin, fframes;          // stft / istft staging
     std::map<int, DevBuf> twiddles;        // exp(-2 pi i j / N) tables by N
     std::vector<void *> hptr;
@@ -79,6 +74,16 @@ struct lwsb_ctx {
         v.mean_amp = mean_amp.as<const double>();
         v.P = P; v.c0 = c0; v.Nreal = Nreal; v.L = L; v.Q = Q; v.B = B;
         return v;
+    }
+    StatScratch scratch() const
+    {
+        return StatScratch{row_max.as<double>(), leaf_tab.as<int>(), leaf_sum.as<double>(), leaf_stride};
+    }
+    LwsbW devw(int which) const
+    {
+        const size_t n = (size_t)w[which].Q * w[which].Q * (w[which].L + 1);
+        const double *d = raww[which].as<const double>();
+        return LwsbW{d, d + n, reinterpret_cast<const int *>(d + 2 * n)};
     }
 };
 
@@ -105,47 +110,6 @@ int fold_for(int Q, int flags)
 {
     if (flags & LWSB_FORCE_ANYQ) return LWSB_FOLD_ANY;
     return Q == 2 ? LWSB_FOLD_Q2 : (Q == 4 ? LWSB_FOLD_Q4 : LWSB_FOLD_ANY); // lws.pyx:246-253
-}
-
-// builds (or fetches) the device copy of a stencil
-int get_stencil(lwsb_ctx *c, int which, int fold, int rframe, int cframe, LwsbStencil *out)
-{
-    auto key = std::make_tuple(which, fold, rframe, cframe);
-    auto it = c->stencils.find(key);
-    if (it == c->stencils.end()) {
-        const WeightSet &w = c->w[which];
-        if (!w.valid()) return fail(c, LWSB_ERR_STATE, "weight set not loaded");
-        const int Q = w.Q, maxt = (2 * Q - 1) * (2 * w.L + 1);
-        std::vector<LwsbTerm> all((size_t)Q * maxt, LwsbTerm{0, 0, 0.0, 0.0});
-        std::vector<int> cnt(Q, 0);
-        for (int p = 0; p < Q; ++p) {
-            std::vector<LwsbTerm> t;
-            build_terms(w, fold, rframe, cframe, p, t);
-            cnt[p] = (int)t.size();
-            std::copy(t.begin(), t.end(), all.begin() + (size_t)p * maxt);
-        }
-        StencilDev sd;
-        sd.maxt = maxt;
-        CU(c, sd.terms.reserve(all.size() * sizeof(LwsbTerm)));
-        CU(c, sd.count.reserve(cnt.size() * sizeof(int)));
-        CU(c, cudaMemcpyAsync(sd.terms.p, all.data(), all.size() * sizeof(LwsbTerm), cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemcpyAsync(sd.count.p, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream)); // host vectors go out of scope
-        it = c->stencils.emplace(key, sd).first;
-    }
-    *out = it->second.view();
-    return LWSB_OK;
-}
-
-void drop_stencils(lwsb_ctx *c, int which)
-{
-    for (auto it = c->stencils.begin(); it != c->stencils.end();) {
-        if (std::get<0>(it->first) == which) {
-            it->second.terms.release();
-            it->second.count.release();
-            it = c->stencils.erase(it);
-        } else ++it;
-    }
 }
 
 int upload_thresholds(lwsb_ctx *c, const double *thr, int n)
@@ -216,11 +180,11 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
     CHECK_CTX(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 3; ++i) drop_stencils(c, i);
-    for (DevBuf *b : {&c->E, &c->A, &c->row_sum, &c->row_max, &c->mean_amp, &c->max_amp, &c->dT, &c->drowbase,
-                      &c->stage, &c->dptr, &c->dthr, &c->dsts, &c->flags, &c->fx, &c->fS, &c->fwin, &c->fframes})
+    for (DevBuf *b : {&c->E, &c->A, &c->row_max, &c->leaf_tab, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
+                      &c->drowbase, &c->stage, &c->dptr, &c->dthr, &c->flags, &c->fx, &c->fS, &c->fwin, &c->fframes})
         b->release();
     for (auto &kv : c->twiddles) kv.second.release();
+    for (int i = 0; i < 3; ++i) c->raww[i].release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -250,7 +214,15 @@ extern "C" int lwsb_set_weights(lwsb_ctx *c, int which, const double *wr, const 
     const size_t n = (size_t)Q * Q * (L + 1);
     w.wr.assign(wr, wr + n);
     w.wi.assign(wi, wi + n);
-    drop_stencils(c, which);
+    // raw copy for the kernels that restate a reference variant literally (NoFuture_LWSQ4)
+    std::vector<int> wf(n);
+    for (size_t i = 0; i < n; ++i) wf[i] = std::hypot(wr[i], wi[i]) > 1.0e-12 ? 1 : 0; // lws.pyx:231-232
+    CU(c, c->raww[which].reserve(2 * n * sizeof(double) + n * sizeof(int)));
+    char *d = c->raww[which].as<char>();
+    CU(c, cudaMemcpyAsync(d, wr, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + n * sizeof(double), wi, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + 2 * n * sizeof(double), wf.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     return LWSB_OK;
 }
 
@@ -323,8 +295,12 @@ extern "C" int lwsb_load(lwsb_ctx *c, const void *const *S_in, const int *T, int
     }
     CU(c, c->E.reserve((size_t)rows * P * sizeof(double2)));
     CU(c, c->A.reserve((size_t)rows * P * sizeof(double)));
-    CU(c, c->row_sum.reserve((size_t)rows * sizeof(double)));
     CU(c, c->row_max.reserve((size_t)rows * sizeof(double)));
+    long long stride = 0;
+    for (int b = 0; b < B; ++b) stride = std::max(stride, stat_leaves_bound((long long)T[b] * Nreal));
+    CU(c, c->leaf_tab.reserve((size_t)B * stride * 3 * sizeof(int)));
+    CU(c, c->leaf_sum.reserve((size_t)B * stride * sizeof(double)));
+    c->leaf_stride = stride;
     CU(c, c->mean_amp.reserve(B * sizeof(double)));
     CU(c, c->max_amp.reserve(B * sizeof(double)));
     CU(c, c->dT.reserve(B * sizeof(int)));
@@ -351,8 +327,8 @@ extern "C" int lwsb_load(lwsb_ctx *c, const void *const *S_in, const int *T, int
     c->total_rows = rows; c->total_bins = bins;
     c->B = B;
     LwsbView v = c->view();
-    launch_extend(v, kind, c->dptr.as<const void *const>(), c->row_sum.as<double>(), c->row_max.as<double>(),
-                  c->mean_amp.as<double>(), c->max_amp.as<double>(), maxT + 2 * (Q - 1), c->stream);
+    launch_extend(v, kind, c->dptr.as<const void *const>(), c->scratch(), c->mean_amp.as<double>(),
+                  c->max_amp.as<double>(), maxT + 2 * (Q - 1), c->stream);
     c->launches += 2;
     CU(c, cudaGetLastError());
     // rowbase / hptr host vectors are read by the async copies above: make them safe to reuse
@@ -398,10 +374,9 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
     if (iterations == 0) return LWSB_OK; // lws.pyx:219-220
     if (int r = use_device(c)) return r;
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
-    LwsbStencil st;
-    if (int r = get_stencil(c, LWSB_W, fold_for(c->Q, flags), c->Q, 1, &st)) return r;
     if (int r = begin_compute(c)) return r;
-    launch_sweeps_generic(c->view(), st, c->dthr.as<const double>(), iterations, c->stream);
+    launch_sweeps_generic(c->view(), c->devw(LWSB_W), fold_for(c->Q, flags), c->Q, 1, c->dthr.as<const double>(),
+                          iterations, c->stream);
     c->launches += 1;
     return end_compute(c);
 }
@@ -418,16 +393,11 @@ extern "C" int lwsb_nofuture(lwsb_ctx *c, int which, const double *thresholds, i
     if (int r = use_device(c)) return r;
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
     const int fold = fold_for(c->Q, flags);
-    LwsbStencil st;
-    if (fold == LWSB_FOLD_Q4) { // NoFuture_LWSQ4, reproduced as written (lwslib.cpp:538-617)
-        if (int r = get_stencil(c, which, LWSB_FOLD_NF4, 1, 0, &st)) return r;
-        if (int r = begin_compute(c)) return r;
-        launch_nofuture_q4(c->view(), st, c->dthr.as<const double>(), iterations, c->stream);
-    } else {
-        if (int r = get_stencil(c, which, fold, 1, 0, &st)) return r;
-        if (int r = begin_compute(c)) return r;
-        launch_sweeps_generic(c->view(), st, c->dthr.as<const double>(), iterations, c->stream);
-    }
+    if (int r = begin_compute(c)) return r;
+    if (fold == LWSB_FOLD_Q4) // NoFuture_LWSQ4, reproduced as written (lwslib.cpp:538-617)
+        launch_nofuture_q4(c->view(), c->devw(which), c->dthr.as<const double>(), iterations, c->stream);
+    else
+        launch_sweeps_generic(c->view(), c->devw(which), fold, 1, 0, c->dthr.as<const double>(), iterations, c->stream);
     c->launches += 1;
     return end_compute(c);
 }
@@ -446,19 +416,10 @@ extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations
         return fail(c, LWSB_ERR_UNSUPPORTED, "spectrum too wide for the online kernel");
     if (int r = use_device(c)) return r;
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
-    const int fold = fold_for(c->Q, flags), Q = c->Q;
-    // table: [rframe-1] for W with rframe 2..Q (index 0 unused), [Q] = W_ai init, [Q+1] = W_af
-    std::vector<LwsbStencil> sts(Q + 2, LwsbStencil{nullptr, nullptr, 0});
-    for (int rf = 2; rf <= Q; ++rf)
-        if (int r = get_stencil(c, LWSB_W, fold, rf, 1, &sts[rf - 1])) return r;
-    if (int r = get_stencil(c, LWSB_W_AI, fold, 1, 0, &sts[Q])) return r;
-    if (int r = get_stencil(c, LWSB_W_AF, fold, 1, 1, &sts[Q + 1])) return r;
-    CU(c, c->dsts.reserve(sts.size() * sizeof(LwsbStencil)));
-    CU(c, cudaMemcpyAsync(c->dsts.p, sts.data(), sts.size() * sizeof(LwsbStencil), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    const LwsbW w3[3] = {c->devw(LWSB_W), c->devw(LWSB_W_AI), c->devw(LWSB_W_AF)};
     if (int r = begin_compute(c)) return r;
-    launch_online_generic(c->view(), c->dsts.as<const LwsbStencil>(), c->dthr.as<const double>(), iterations,
-                          look_ahead, c->stream);
+    launch_online_generic(c->view(), w3, fold_for(c->Q, flags), c->dthr.as<const double>(), iterations, look_ahead,
+                          c->stream);
     c->launches += 1;
     return end_compute(c);
 }
@@ -468,8 +429,8 @@ extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations
 // recomputed from the updated values.
 static int restage(lwsb_ctx *c)
 {
-    launch_reextend(c->view(), c->row_sum.as<double>(), c->row_max.as<double>(), c->mean_amp.as<double>(),
-                    c->max_amp.as<double>(), c->maxT + 2 * (c->Q - 1), c->stream);
+    launch_reextend(c->view(), c->scratch(), c->mean_amp.as<double>(), c->max_amp.as<double>(),
+                    c->maxT + 2 * (c->Q - 1), c->stream);
     c->launches += 3;
     CU(c, cudaGetLastError());
     return LWSB_OK;

@@ -2,20 +2,30 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "lwsb_common.h"
+#include "exact.cuh"
 
 namespace lwsb {
 
 // kernels_generic.cu
-void launch_extend(const LwsbView &v, int kind, const void *const *src, double *row_sum, double *row_max,
-                   double *mean_amp, double *max_amp, int maxTp, cudaStream_t s);
+struct StatScratch {     // work space of the numpy-ordered mean (k_stats)
+    double *row_max;     // [total rows]
+    int *leaf_tab;       // [B][stride][3]
+    double *leaf_sum;    // [B][stride]
+    long long stride;    // leaves reserved per utterance
+};
+inline long long stat_leaves_bound(long long n) { return n / 32 + 8; } // leaves hold > 32 elements once n > 128
+
+void launch_extend(const LwsbView &v, int kind, const void *const *src, const StatScratch &sc, double *mean_amp,
+                   double *max_amp, int maxTp, cudaStream_t s);
 void launch_refresh_ghosts(const LwsbView &v, cudaStream_t s);
-void launch_reextend(const LwsbView &v, double *row_sum, double *row_max, double *mean_amp, double *max_amp,
-                     int maxTp, cudaStream_t s);
+void launch_reextend(const LwsbView &v, const StatScratch &sc, double *mean_amp, double *max_amp, int maxTp,
+                     cudaStream_t s);
 void launch_crop(const LwsbView &v, void *const *dst, int maxT, cudaStream_t s);
-void launch_sweeps_generic(const LwsbView &v, const LwsbStencil &st, const double *thr, int iters, cudaStream_t s);
-void launch_online_generic(const LwsbView &v, const LwsbStencil *sts, const double *thr, int iters, int LA,
+void launch_sweeps_generic(const LwsbView &v, const LwsbW &w, int fold, int rframe, int cframe, const double *thr,
+                           int iters, cudaStream_t s);
+void launch_online_generic(const LwsbView &v, const LwsbW *w3, int fold, const double *thr, int iters, int LA,
                            cudaStream_t s);
-void launch_nofuture_q4(const LwsbView &v, const LwsbStencil &st, const double *thr, int iters, cudaStream_t s);
+void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, int iters, cudaStream_t s);
 
 // kernels_fft.cu
 cudaError_t launch_stft(const double *x, int B, int nsamples, const double *awin, int fsize, int hop, int N, int logN,

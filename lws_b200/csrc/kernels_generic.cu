@@ -7,12 +7,14 @@
 // update number j of a chain at "time" c + (L+1)*j therefore reproduces the sequential result
 // exactly; successive sweeps may follow each other Q frames apart.
 // The generic kernels run one CTA per utterance in lock step (one bin per row update per
-// step, __syncthreads between steps) with the state in global memory.  They are the
-// reference-exact fallback for every configuration; the tuned batch kernel lives in
+// step, __syncthreads between steps) with the state in global memory.  Every bin is computed
+// with the reference's own operation sequence (exact.cuh), so results are bit-identical to
+// the CPU reference.  They serve every configuration; the tuned batch kernel lives in
 // kernels_batch.cu.
 #include <cuda_runtime.h>
 #include "lwsb_common.h"
 #include "kernels.h"
+#include "exact.cuh"
 
 namespace lwsb {
 
@@ -20,7 +22,7 @@ namespace lwsb {
 // extend + amplitude + per-frame statistics   (lws.pyx:146-157, 235-240; lwslib.cpp:15-65)
 // grid (max Tp, B), one CTA per extended row.
 template <int KIND>
-__global__ void k_extend(LwsbView v, const void *const *src, double *row_sum, double *row_max)
+__global__ void k_extend(LwsbView v, const void *const *src, double *row_max)
 {
     const int u = blockIdx.y;
     const int T = v.T[u];
@@ -34,7 +36,7 @@ __global__ void k_extend(LwsbView v, const void *const *src, double *row_sum, do
     double2 *E = v.E + row * v.P;
     double *A = v.A + row * v.P;
     const int e0 = v.c0 - L; // physical column of extended column 0
-    double s = 0.0, mx = 0.0;
+    double mx = 0.0;
     for (int x = threadIdx.x; x < v.P; x += blockDim.x) {
         const int c = x - v.c0; // bin index, may be a mirrored one
         double2 val = make_double2(0.0, 0.0);
@@ -47,55 +49,117 @@ __global__ void k_extend(LwsbView v, const void *const *src, double *row_sum, do
             if (KIND == 0) {
                 const double2 *S = reinterpret_cast<const double2 *>(src[u]);
                 val = S[(long long)p * Nreal + cs];
-                a = hypot(val.x, val.y);
+                a = x_cabs(val.x, val.y); // np.abs(ExtS), lws.pyx:239
             } else {
                 const double *S = reinterpret_cast<const double *>(src[u]);
                 val = make_double2(S[(long long)p * Nreal + cs], 0.0);
                 a = fabs(val.x);
             }
             if (cj) val.y = -val.y;
-            if (c >= 0 && c < Nreal) { s += a; mx = fmax(mx, a); }
+            if (c >= 0 && c < Nreal) mx = fmax(mx, a);
         }
         E[x] = val;
         A[x] = a;
     }
-    // deterministic block reduction (fixed tree): the mean must not depend on scheduling
-    __shared__ double sh_s[32], sh_m[32];
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_down_sync(0xffffffffu, s, o);
-        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    }
+    // per-frame maximum of |S| (the mean is summed separately, in numpy's order: k_stats)
+    __shared__ double sh_m[32];
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
     const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if ((threadIdx.x & 31) == 0) { sh_s[w] = s; sh_m[w] = mx; }
+    if ((threadIdx.x & 31) == 0) sh_m[w] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double ts = 0.0, tm = 0.0;
-        for (int i = 0; i < nw; ++i) { ts += sh_s[i]; tm = fmax(tm, sh_m[i]); }
-        row_sum[row] = ts;
+        double tm = 0.0;
+        for (int i = 0; i < nw; ++i) tm = fmax(tm, sh_m[i]);
         row_max[row] = tm;
     }
 }
 
-// mean / max of |S| over the un-extended spectrogram (lws.pyx:240); grid B
-__global__ void k_stats(LwsbView v, const double *row_sum, const double *row_max, double *mean_amp, double *max_amp)
+// mean / max of |S| over the un-extended spectrogram (lws.pyx:240); grid B.
+// `mean_amp = np.mean(np.abs(S))` is numpy's *pairwise* summation of the row-major flattened
+// array (numpy/_core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum: blocks of <= 128
+// elements summed with 8 interleaved accumulators, halves split at a multiple of 8) divided by
+// the element count.  The thresholds are multiples of this number and the comparison
+// `absspec > threshold` (lwslib.cpp:296) decides which bins move, so the sum is reproduced
+// in the same order: thread 0 walks the recursion and emits the leaf blocks plus, per leaf, how
+// many pending partial sums to combine after it; all threads sum leaves; thread 0 combines.
+__device__ __forceinline__ double amp_at(const LwsbView &v, long long row0, long long i)
+{
+    const long long r = i / v.Nreal;
+    const int c = (int)(i - r * v.Nreal);
+    return v.A[(row0 + r) * v.P + v.c0 + c];
+}
+
+__global__ void __launch_bounds__(256)
+k_stats(LwsbView v, const double *row_max, double *mean_amp, double *max_amp, int *leaf_tab, double *leaf_sum,
+        long long scratch_stride)
 {
     const int u = blockIdx.x;
     const int T = v.T[u];
-    const long long r0 = v.rowbase[u] + (v.Q - 1);
-    double s = 0.0, mx = 0.0;
-    for (int m = threadIdx.x; m < T; m += blockDim.x) { s += row_sum[r0 + m]; mx = fmax(mx, row_max[r0 + m]); }
-    __shared__ double sh_s[32], sh_m[32];
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_down_sync(0xffffffffu, s, o);
-        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    const long long row0 = v.rowbase[u] + (v.Q - 1);
+    const long long n = (long long)T * v.Nreal;
+    int *tab = leaf_tab + (size_t)u * scratch_stride * 3; // (offset, length, adds-after) per leaf
+    double *ls = leaf_sum + (size_t)u * scratch_stride;
+    __shared__ int n_leaves;
+    __shared__ double sh_m[32];
+    if (threadIdx.x == 0) {
+        // post-order walk of pairwise(a, n) = n <= 128 ? leaf : pairwise(a, n2) + pairwise(a + n2, n - n2)
+        long long off[64], len[64];
+        int state[64], sp = 0, nl = 0;
+        off[0] = 0; len[0] = n; state[0] = 0; sp = 1;
+        while (sp > 0) {
+            const int top = sp - 1;
+            if (len[top] <= 128) {
+                tab[3 * nl] = (int)off[top]; tab[3 * nl + 1] = (int)len[top]; tab[3 * nl + 2] = 0;
+                ++nl; --sp;
+            } else if (state[top] == 0) {
+                long long n2 = len[top] / 2; n2 -= n2 % 8;
+                state[top] = 1;
+                // right child is pushed first so that the left one is processed first
+                off[sp] = off[top] + n2; len[sp] = len[top] - n2; state[sp] = 0; ++sp;
+                off[sp] = off[top]; len[sp] = n2; state[sp] = 0; ++sp;
+            } else {
+                tab[3 * (nl - 1) + 2] += 1; // both children done: one addition after the last leaf emitted
+                --sp;
+            }
+        }
+        n_leaves = nl;
     }
+    __syncthreads();
+    for (int l = threadIdx.x; l < n_leaves; l += blockDim.x) {
+        const long long lo = tab[3 * l];
+        const int m = tab[3 * l + 1];
+        double res;
+        if (m < 8) {
+            res = 0.0;
+            for (int i = 0; i < m; ++i) res = __dadd_rn(res, amp_at(v, row0, lo + i));
+        } else {
+            double r[8];
+            for (int j = 0; j < 8; ++j) r[j] = amp_at(v, row0, lo + j);
+            int i = 8;
+            for (; i < m - (m % 8); i += 8)
+                for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], amp_at(v, row0, lo + i + j));
+            res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+            for (; i < m; ++i) res = __dadd_rn(res, amp_at(v, row0, lo + i));
+        }
+        ls[l] = res;
+    }
+    double mx = 0.0;
+    for (int m = threadIdx.x; m < T; m += blockDim.x) mx = fmax(mx, row_max[row0 + m]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
     const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if ((threadIdx.x & 31) == 0) { sh_s[w] = s; sh_m[w] = mx; }
+    if ((threadIdx.x & 31) == 0) sh_m[w] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double ts = 0.0, tm = 0.0;
-        for (int i = 0; i < nw; ++i) { ts += sh_s[i]; tm = fmax(tm, sh_m[i]); }
-        mean_amp[u] = ts / ((double)T * (double)v.Nreal);
+        double st[64];
+        int sp = 0;
+        for (int l = 0; l < n_leaves; ++l) {
+            st[sp++] = ls[l];
+            for (int a = tab[3 * l + 2]; a > 0; --a) { st[sp - 2] = __dadd_rn(st[sp - 2], st[sp - 1]); --sp; }
+        }
+        mean_amp[u] = __ddiv_rn(st[0], (double)n); // umr_sum(...) / count  (numpy _methods._mean)
+        double tm = 0.0;
+        for (int i = 0; i < nw; ++i) tm = fmax(tm, sh_m[i]);
         max_amp[u] = tm;
     }
 }
@@ -120,7 +184,7 @@ __global__ void k_refresh_ghosts(LwsbView v)
 // Recompute |E| and the per-frame statistics of the real frames from the CURRENT values: the
 // `AmpSpec = np.abs(ExtS)` / `mean_amp` of the next chained reference call (lws.pyx:239-240).
 // grid (max Tp, B)
-__global__ void k_reamp(LwsbView v, double *row_sum, double *row_max)
+__global__ void k_reamp(LwsbView v, double *row_max)
 {
     const int u = blockIdx.y;
     const int T = v.T[u];
@@ -130,26 +194,22 @@ __global__ void k_reamp(LwsbView v, double *row_sum, double *row_max)
     const double2 *E = v.E + row * v.P;
     double *A = v.A + row * v.P;
     const int e0 = v.c0 - v.L, Np = v.Nreal + 2 * v.L;
-    double s = 0.0, mx = 0.0;
+    double mx = 0.0;
     for (int e = threadIdx.x; e < Np; e += blockDim.x) {
         const double2 val = E[e0 + e];
-        const double a = hypot(val.x, val.y);
+        const double a = x_cabs(val.x, val.y);
         A[e0 + e] = a;
         const int c = e - v.L;
-        if (c >= 0 && c < v.Nreal) { s += a; mx = fmax(mx, a); }
+        if (c >= 0 && c < v.Nreal) mx = fmax(mx, a);
     }
-    __shared__ double sh_s[32], sh_m[32];
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_down_sync(0xffffffffu, s, o);
-        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    }
+    __shared__ double sh_m[32];
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
     const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if ((threadIdx.x & 31) == 0) { sh_s[w] = s; sh_m[w] = mx; }
+    if ((threadIdx.x & 31) == 0) sh_m[w] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double ts = 0.0, tm = 0.0;
-        for (int i = 0; i < nw; ++i) { ts += sh_s[i]; tm = fmax(tm, sh_m[i]); }
-        row_sum[row] = ts;
+        double tm = 0.0;
+        for (int i = 0; i < nw; ++i) tm = fmax(tm, sh_m[i]);
         row_max[row] = tm;
     }
 }
@@ -166,13 +226,25 @@ __global__ void k_crop(LwsbView v, void *const *dst)
 }
 
 // ------------------------------------------------------------------------------------------
-// one bin update, generic stencil
-__device__ __forceinline__ void commit_bin(const LwsbView &v, double2 *Erow, int c, double tr, double ti, double a)
+// one bin update on the global-memory state, reference arithmetic (exact.cuh)
+struct GlobalCell {
+    const double2 *ctr; // &E[m][n]
+    int P;
+    __device__ __forceinline__ double2 operator()(int dr, int dk) const { return ctr[(long long)dr * P + dk]; }
+};
+
+__device__ __forceinline__ void update_bin(const LwsbView &v, const LwsbW &w, int fold, int rframe, int cframe,
+                                           long long row, int c, double thr)
 {
-    // lwslib.cpp:356-368: normalise to the stored magnitude, refresh the mirrored copies at once
-    const double mag = sqrt(tr * tr + ti * ti);
-    if (mag > 0.0) {
-        const double2 val = make_double2(tr * a / mag, ti * a / mag);
+    double2 *Erow = v.E + row * v.P;
+    const double a = v.A[row * v.P + v.c0 + c];
+    if (!(a > thr)) return; // lwslib.cpp:295-296
+    const GlobalCell cell{Erow + v.c0 + c, v.P};
+    double tr, ti;
+    x_weighted_sum(cell, w, v.Q, v.L, c % v.Q, fold, rframe, cframe, tr, ti);
+    double2 val;
+    if (x_project(tr, ti, a, val)) {
+        // lwslib.cpp:356-368: store, then refresh the mirrored copies at once
         Erow[v.c0 + c] = val;
         const int Nreal = v.Nreal;
         if (c >= 1 && c <= v.L) Erow[v.c0 - c] = make_double2(val.x, -val.y);
@@ -180,30 +252,11 @@ __device__ __forceinline__ void commit_bin(const LwsbView &v, double2 *Erow, int
     }
 }
 
-__device__ __forceinline__ void update_bin(const LwsbView &v, const LwsbStencil &st, long long row, int c, double thr)
-{
-    double2 *Erow = v.E + row * v.P;
-    const double a = v.A[row * v.P + v.c0 + c];
-    if (!(a > thr)) return; // lwslib.cpp:295-296
-    const int p = c % v.Q;
-    const LwsbTerm *tm = st.terms + (size_t)p * st.maxt;
-    const int cnt = st.count[p];
-    double tr = 0.0, ti = 0.0;
-    const double2 *ctr = Erow + v.c0 + c;
-    for (int e = 0; e < cnt; ++e) {
-        const LwsbTerm t = tm[e];
-        const double2 x = ctr[(long long)t.dr * v.P + t.dk];
-        tr = fma(t.cr, x.x, tr); tr = fma(-t.ci, x.y, tr);
-        ti = fma(t.cr, x.y, ti); ti = fma(t.ci, x.x, ti);
-    }
-    commit_bin(v, Erow, c, tr, ti, a);
-}
-
 // ------------------------------------------------------------------------------------------
 // `iters` pipelined sweeps (batch: rframe Q / cframe 1; no-future: rframe 1 / cframe 0).
 // Sweep i, frame m, bin c runs at step  c + (L+1)*(m + Q*i).  One CTA per utterance.
 __global__ void __launch_bounds__(1024)
-k_sweeps_generic(LwsbView v, LwsbStencil st, const double *thresholds, int iters)
+k_sweeps_generic(LwsbView v, LwsbW w, int fold, int rframe, int cframe, const double *thresholds, int iters)
 {
     const int u = blockIdx.x;
     const int T = v.T[u], Q = v.Q, Nreal = v.Nreal;
@@ -226,7 +279,7 @@ k_sweeps_generic(LwsbView v, LwsbStencil st, const double *thresholds, int iters
             const long long m = vv - (long long)Q * i;
             if (m < 0 || m >= T) continue;
             const int c = (int)(t - S * vv);
-            update_bin(v, st, row0 + m, c, thresholds[i] * mean); // lws.pyx:245
+            update_bin(v, w, fold, rframe, cframe, row0 + m, c, __dmul_rn(thresholds[i], mean)); // lws.pyx:245
         }
         __syncthreads();
     }
@@ -236,7 +289,7 @@ k_sweeps_generic(LwsbView v, LwsbStencil st, const double *thresholds, int iters
 // online (TF-RTISI-LA) chain: row update j of the chain, bin c runs at step c + (L+1)*j.
 // One CTA per utterance; thread k serves the chain positions j == k (mod blockDim).
 __global__ void __launch_bounds__(1024)
-k_online_generic(LwsbView v, const LwsbStencil *sts, const double *thresholds, int iters, int LA)
+k_online_generic(LwsbView v, LwsbW w0, LwsbW w_ai, LwsbW w_af, int fold, const double *thresholds, int iters, int LA)
 {
     const int u = blockIdx.x;
     const int T = v.T[u], Q = v.Q, Nreal = v.Nreal;
@@ -248,7 +301,6 @@ k_online_generic(LwsbView v, const LwsbStencil *sts, const double *thresholds, i
     const int nt = blockDim.x; // >= ceil(Nreal / S) + 1 (launch_online_generic guarantees)
     long long jc = -1;
     LwsbOnlineTask task;
-    LwsbStencil st;
     double thr = 0.0;
     for (long long t = 0; t <= tmax; ++t) {
         const long long jhi = t / S;
@@ -261,10 +313,10 @@ k_online_generic(LwsbView v, const LwsbStencil *sts, const double *thresholds, i
                 if (j != jc) {
                     jc = j;
                     task = lwsb_online_decode(T, iters, LA, Q, j);
-                    st = sts[task.which == 0 ? task.rframe - 1 : (task.which == 1 ? Q : Q + 1)];
-                    thr = task.thr < 0 ? 0.0 : thresholds[task.thr] * mean; // lws.pyx:361, lwslib.cpp:1467
+                    thr = task.thr < 0 ? 0.0 : __dmul_rn(thresholds[task.thr], mean); // lws.pyx:361, lwslib.cpp:1467
                 }
-                update_bin(v, st, base + task.row, (int)c, thr);
+                update_bin(v, task.which == 0 ? w0 : (task.which == 1 ? w_ai : w_af), fold, task.rframe, task.cframe,
+                           base + task.row, (int)c, thr);
             }
         }
         __syncthreads();
@@ -272,45 +324,82 @@ k_online_generic(LwsbView v, const LwsbStencil *sts, const double *thresholds, i
 }
 
 // ------------------------------------------------------------------------------------------
-// NoFuture_LWSQ4 as the reference computes it (lwslib.cpp:538-617): the doubled bin offset
-// makes frame m read up to bin 2c+L of frame m-1 and even the already-updated part of frame
-// m itself, so frames cannot be skewed by a constant; the (single) sweep is run in raster
-// order by one warp per utterance with the <= 3*(2L+1) stencil terms spread over the lanes.
-__global__ void __launch_bounds__(32)
-k_nofuture_q4(LwsbView v, LwsbStencil st, const double *thresholds, int iters)
+// NoFuture_LWSQ4 as the reference computes it (lwslib.cpp:538-617).  `im` already contains the
+// bin index and the reads add it again, so bin n of frame m reads the flat offsets
+// (m-r)*Np + 2n +- k: frames m-3 .. m-1 at doubled bin positions and, for the upper half of the
+// spectrum, the already-updated part of frame m itself (mirror cells included).
+//
+// This map is numerically *expanding* (a 1e-16 perturbation grows by ~2x per frame: measured,
+// DESIGN.md), so parity needs the reference's arithmetic bit for bit: every product and sum is
+// rounded separately (no FMA contraction -- the reference's x86-64 build has none), terms are
+// added in the reference's order (r = 3,2,1; k = 1..L, then k = 0), |.| is
+// sqrt(x*x + y*y) and the normalisation is (t * a) / |t|.
+//
+// Schedule: one CTA per utterance, frames in order.  Inside a frame bin n depends on the
+// current frame only through columns <= 2n + L - Np (and, through the mirror cells, on bins
+// <= 2L), so the frame is processed in waves: first every bin below (Np-L)/2 at once, then the
+// remaining distance to the end of the frame halves with every wave (~log2 Np waves per frame).
+__device__ __forceinline__ double2 nf4_load(const double2 *E0, int P, int Np, int row, int off)
+{
+    // flat offset row*Np + off of the reference layout, 0 <= off < 2*Np
+    if (off >= Np) { off -= Np; row += 1; }
+    return E0[(long long)row * P + off];
+}
+
+__global__ void __launch_bounds__(512)
+k_nofuture_q4(LwsbView v, const double *wr, const double *wi, const int *wf, const double *thresholds, int iters)
 {
     const int u = blockIdx.x;
-    const int T = v.T[u], Q = v.Q, Nreal = v.Nreal, L = v.L;
-    const int Np = Nreal + 2 * L;
-    const int lane = threadIdx.x;
+    const int T = v.T[u], Nreal = v.Nreal, L = v.L;
+    constexpr int Q = 4;
+    const int Np = Nreal + 2 * L, Naux = Nreal + L - 1, P = v.P;
     const double mean = v.mean_amp[u];
-    double2 *E0 = v.E + v.rowbase[u] * v.P + (v.c0 - L); // extended (row 0, column 0)
+    double2 *E0 = v.E + v.rowbase[u] * (long long)P + (v.c0 - L); // extended (row 0, column 0)
+    const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
+    const int lim1 = (Np - L + 1) / 2; // first n whose reads reach the current frame
     for (int it = 0; it < iters; ++it) {
-        const double thr = thresholds[it] * mean;
+        const double thr = __dmul_rn(thresholds[it], mean); // lws.pyx:298
         for (int m = Q - 1; m < T + Q - 1; ++m) {
-            double2 *Erow = v.E + (v.rowbase[u] + m) * v.P;
-            const double *Arow = v.A + (v.rowbase[u] + m) * v.P;
-            for (int c = 0; c < Nreal; ++c) {
-                const double a = Arow[v.c0 + c];
-                if (!(a > thr)) continue;
-                const int p = c % Q;
-                const LwsbTerm *tm = st.terms + (size_t)p * st.maxt;
-                const int cnt = st.count[p];
-                double tr = 0.0, ti = 0.0;
-                for (int e = lane; e < cnt; e += 32) {
-                    const LwsbTerm t = tm[e];
-                    const long long f = (long long)(m + t.dr) * Np + 2 * (c + L) + t.dk; // reference flat offset
-                    const long long fr = f / Np, fc = f % Np;
-                    const double2 x = E0[fr * v.P + fc];
-                    tr = fma(t.cr, x.x, tr); tr = fma(-t.ci, x.y, tr);
-                    ti = fma(t.cr, x.y, ti); ti = fma(t.ci, x.x, ti);
+            int done = L;
+            while (done <= Naux) {
+                int hi = (2 * L < done) ? (done + Np - L + 1) / 2 : lim1;
+                if (hi < done + 1) hi = done + 1;
+                if (hi > Naux + 1) hi = Naux + 1;
+                for (int n = done + threadIdx.x; n < hi; n += blockDim.x) {
+                    const double a = A0[(long long)m * P + n];
+                    if (!(a > thr)) continue;
+                    double tr = 0.0, ti = 0.0;
+                    const int wp = ((n - L) % Q) * Q * (L + 1);
+                    for (int r = Q - 1; r > 0; --r) {
+                        const int wu = wp + r * (L + 1);
+                        const bool minus = ((n - L) & 1) && (r & 1);
+                        for (int k = 1; k <= L; ++k) {
+                            if (!wf[wu + k]) continue;
+                            const double ar = wr[wu + k], ai = wi[wu + k];
+                            const double2 b = nf4_load(E0, P, Np, m - r, 2 * n - k);
+                            double2 c = nf4_load(E0, P, Np, m - r, 2 * n + k);
+                            if (minus) { c.x = -c.x; c.y = -c.y; }
+                            tr = __dadd_rn(tr, __dsub_rn(__dmul_rn(ar, __dadd_rn(b.x, c.x)), __dmul_rn(ai, __dsub_rn(b.y, c.y))));
+                            ti = __dadd_rn(ti, __dadd_rn(__dmul_rn(ar, __dadd_rn(b.y, c.y)), __dmul_rn(ai, __dsub_rn(b.x, c.x))));
+                        }
+                        if (wf[wu]) {
+                            const double ar = wr[wu], ai = wi[wu];
+                            const double2 b = nf4_load(E0, P, Np, m - r, 2 * n);
+                            tr = __dadd_rn(tr, __dsub_rn(__dmul_rn(ar, b.x), __dmul_rn(ai, b.y)));
+                            ti = __dadd_rn(ti, __dadd_rn(__dmul_rn(ar, b.y), __dmul_rn(ai, b.x)));
+                        }
+                    }
+                    const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(tr, tr), __dmul_rn(ti, ti)));
+                    if (mag > 0.0) {
+                        const double2 val = make_double2(__ddiv_rn(__dmul_rn(tr, a), mag), __ddiv_rn(__dmul_rn(ti, a), mag));
+                        double2 *Erow = E0 + (long long)m * P;
+                        Erow[n] = val;
+                        if (n >= L + 1 && n < 2 * L + 1) Erow[2 * L - n] = make_double2(val.x, -val.y);
+                        else if (n >= Nreal - 1 && n < Naux) Erow[2 * Naux - n] = make_double2(val.x, -val.y);
+                    }
                 }
-                for (int o = 16; o > 0; o >>= 1) {
-                    tr += __shfl_xor_sync(0xffffffffu, tr, o);
-                    ti += __shfl_xor_sync(0xffffffffu, ti, o);
-                }
-                if (lane == 0) commit_bin(v, Erow, c, tr, ti, a);
-                __syncwarp();
+                __syncthreads();
+                done = hi;
             }
         }
     }
@@ -318,13 +407,13 @@ k_nofuture_q4(LwsbView v, LwsbStencil st, const double *thresholds, int iters)
 
 // ------------------------------------------------------------------------------------------
 // launch wrappers
-void launch_extend(const LwsbView &v, int kind, const void *const *src, double *row_sum, double *row_max,
-                   double *mean_amp, double *max_amp, int maxTp, cudaStream_t s)
+void launch_extend(const LwsbView &v, int kind, const void *const *src, const StatScratch &sc, double *mean_amp,
+                   double *max_amp, int maxTp, cudaStream_t s)
 {
     dim3 grid(maxTp, v.B);
-    if (kind == 0) k_extend<0><<<grid, 256, 0, s>>>(v, src, row_sum, row_max);
-    else k_extend<1><<<grid, 256, 0, s>>>(v, src, row_sum, row_max);
-    k_stats<<<v.B, 256, 0, s>>>(v, row_sum, row_max, mean_amp, max_amp);
+    if (kind == 0) k_extend<0><<<grid, 256, 0, s>>>(v, src, sc.row_max);
+    else k_extend<1><<<grid, 256, 0, s>>>(v, src, sc.row_max);
+    k_stats<<<v.B, 256, 0, s>>>(v, sc.row_max, mean_amp, max_amp, sc.leaf_tab, sc.leaf_sum, sc.stride);
 }
 
 void launch_refresh_ghosts(const LwsbView &v, cudaStream_t s)
@@ -334,13 +423,13 @@ void launch_refresh_ghosts(const LwsbView &v, cudaStream_t s)
     k_refresh_ghosts<<<grid, 256, 0, s>>>(v);
 }
 
-void launch_reextend(const LwsbView &v, double *row_sum, double *row_max, double *mean_amp, double *max_amp,
-                     int maxTp, cudaStream_t s)
+void launch_reextend(const LwsbView &v, const StatScratch &sc, double *mean_amp, double *max_amp, int maxTp,
+                     cudaStream_t s)
 {
     dim3 grid(maxTp, v.B);
-    k_reamp<<<grid, 256, 0, s>>>(v, row_sum, row_max);
+    k_reamp<<<grid, 256, 0, s>>>(v, sc.row_max);
     launch_refresh_ghosts(v, s);
-    k_stats<<<v.B, 256, 0, s>>>(v, row_sum, row_max, mean_amp, max_amp);
+    k_stats<<<v.B, 256, 0, s>>>(v, sc.row_max, mean_amp, max_amp, sc.leaf_tab, sc.leaf_sum, sc.stride);
 }
 
 void launch_crop(const LwsbView &v, void *const *dst, int maxT, cudaStream_t s)
@@ -349,22 +438,27 @@ void launch_crop(const LwsbView &v, void *const *dst, int maxT, cudaStream_t s)
     k_crop<<<grid, 256, 0, s>>>(v, dst);
 }
 
-void launch_sweeps_generic(const LwsbView &v, const LwsbStencil &st, const double *thr, int iters, cudaStream_t s)
+void launch_sweeps_generic(const LwsbView &v, const LwsbW &w, int fold, int rframe, int cframe, const double *thr,
+                           int iters, cudaStream_t s)
 {
-    k_sweeps_generic<<<v.B, 1024, 0, s>>>(v, st, thr, iters);
+    k_sweeps_generic<<<v.B, 1024, 0, s>>>(v, w, fold, rframe, cframe, thr, iters);
 }
 
-void launch_online_generic(const LwsbView &v, const LwsbStencil *sts, const double *thr, int iters, int LA,
+void launch_online_generic(const LwsbView &v, const LwsbW *w3, int fold, const double *thr, int iters, int LA,
                            cudaStream_t s)
 {
     int nt = (v.Nreal + v.L) / (v.L + 1) + 1;
     nt = (nt + 31) / 32 * 32;
-    k_online_generic<<<v.B, nt, 0, s>>>(v, sts, thr, iters, LA);
+    k_online_generic<<<v.B, nt, 0, s>>>(v, w3[0], w3[1], w3[2], fold, thr, iters, LA);
 }
 
-void launch_nofuture_q4(const LwsbView &v, const LwsbStencil &st, const double *thr, int iters, cudaStream_t s)
+void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, int iters, cudaStream_t s)
 {
-    k_nofuture_q4<<<v.B, 32, 0, s>>>(v, st, thr, iters);
+    const double *wr = w.wr, *wi = w.wi;
+    const int *wf = w.wf;
+    int nt = (v.Nreal + 2 * v.L) / 2 + 32;
+    nt = nt > 512 ? 512 : (nt + 31) / 32 * 32;
+    k_nofuture_q4<<<v.B, nt, 0, s>>>(v, wr, wi, wf, thr, iters);
 }
 
 } // namespace lwsb

@@ -47,7 +47,33 @@ def extspec(S, L, Q):
 
 
 def create_weights(awin, swin, fshift, L, use_summarized_weights=True):
-    """Complex LWS weights, shape (Qprime, Q, L+1) (lws.pyx:160-181)."""
+    """Complex LWS weights, shape (Qprime, Q, L+1) (lws.pyx:160-181).
+
+    Evaluated with the same numpy operations as the reference (complex exponential tables, a
+    BLAS ``dot`` with the window products, two broadcast multiplications): the LWS iteration
+    is sensitive to the last bit of these 96..384 numbers ("why bit-exact"), and a
+    BLAS dot cannot be reproduced natively.  ``lwsb_create_weights`` in the C-ABI is the host
+    C++ twin (equal to ~1e-16); the class uses this one so that results match the reference
+    bit for bit."""
+    T = len(awin)
+    Q = int(np.ceil(float(T) / float(fshift)))
+    Qfloat = float(T) / float(fshift)
+    Qprime = Q if (T % fshift == 0 and use_summarized_weights) else T
+    kcol = np.atleast_2d(np.arange(L + 1)).T
+    dft_rows = np.exp(-1j * 2 * np.pi * kcol * np.arange(T) / T)
+    winprod = np.zeros((T, Q))
+    for q in range(Q):
+        t = np.arange(T - q * fshift)
+        winprod[t, q] = awin[t] * swin[t + q * fshift] / T
+    W = (dft_rows.dot(winprod)) * np.exp(-1j * 2 * np.pi * kcol * np.arange(Q) / Qfloat)
+    W[0, 0] = W[0, 0] - 1
+    phase = np.exp(1j * 2 * np.pi * np.atleast_2d(np.arange(Qprime)).T * np.arange(Q) / Qfloat)
+    W = W[:, np.newaxis] * phase[np.newaxis, :]
+    return W.transpose((1, 2, 0))
+
+
+def create_weights_native(awin, swin, fshift, L, use_summarized_weights=True):
+    """The C-ABI's host C++ version of the same table (lwsb_create_weights)."""
     return _native.create_weights(awin, swin, fshift, L, use_summarized_weights)
 
 
