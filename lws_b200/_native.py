@@ -47,9 +47,12 @@ SIGNATURES = {
     "lwsb_istft": (_ci, [_vp, _vp, _ci, _ci, _ci, _dp, _ci, _ci, _vp, _ci]),
     "lwsb_last_compute_ms": (_ci, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "lwsb_launch_count": (_ll, [_vp]),
+    "lwsb_last_batch_plan": (_ci, [_vp, _ip]),
     "lwsb_device_info": (_ci, [_vp, _ip, _ip, _ip, ctypes.POINTER(_ll)]),
     "lwsb_get_stats": (_ci, [_vp, _dp, _dp]),
     "lwsb_debug_terms": (_ci, [_dp, _dp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ip, _ip, _dp, _dp]),
+    "lwsb_debug_plan_strips": (_ci, [_ci, _ci, _ci, _ci, _ci, _ci, _ll, _ci, _ci, _ci, _ip]),
+    "lwsb_set_tuning": (_ci, [_vp, _ll, _ci, _ci]),
     "lwsb_debug_online_chain_length": (_ll, [_ci, _ci, _ci]),
     "lwsb_debug_online_task": (_ci, [_ci, _ci, _ci, _ci, _ll, _ip, _ip, _ip, _ip, _ip]),
 }
@@ -251,6 +254,18 @@ class Context(object):
         self._c(lib().lwsb_last_compute_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
 
+    def set_tuning(self, smem_limit=0, cluster=0, sweeps_per_pass=0):
+        self._c(lib().lwsb_set_tuning(self._h, int(smem_limit), int(cluster), int(sweeps_per_pass)))
+
+    def last_batch_plan(self):
+        """dict describing the cluster strip plan of the last batch() call, or None (generic kernel)."""
+        out = (ctypes.c_int * 9)()
+        if self._c(lib().lwsb_last_batch_plan(self._h, out)) != 1:
+            return None
+        keys = ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots", "sweeps_per_pass", "ring_rows",
+                "ring_pitch", "threads", "smem_bytes")
+        return dict(zip(keys, list(out)))
+
     def launch_count(self):
         return int(lib().lwsb_launch_count(self._h))
 
@@ -278,6 +293,18 @@ def debug_terms(Wc, fold, rframe, cframe, p):
     n = _check(lib().lwsb_debug_terms(_dptr(wr), _dptr(wi), Q, L, fold, rframe, cframe, p, mx, dr.ctypes.data_as(_ip),
                                       dk.ctypes.data_as(_ip), _dptr(cr), _dptr(ci)))
     return dr[:n], dk[:n], cr[:n] + 1j * ci[:n]
+
+
+PLAN_KEYS = ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots", "sweeps_per_pass", "ring_rows",
+             "ring_pitch", "threads", "smem_bytes")
+
+
+def debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit=232448, sm_count=148, cluster=0, sweeps=0):
+    out = (ctypes.c_int * 9)()
+    if _check(lib().lwsb_debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit, sm_count, cluster, sweeps,
+                                           out)) != 1:
+        return None
+    return dict(zip(PLAN_KEYS, list(out)))
 
 
 def debug_online_chain(T, iterations, look_ahead, Q):

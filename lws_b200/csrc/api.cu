@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -59,6 +60,11 @@ struct lwsb_ctx {
     DevBuf E, A, row_max, leaf_tab, leaf_sum, mean_amp, max_amp, dT, drowbase, stage, dptr, dthr, flags;
     long long leaf_stride = 0;
     DevBuf fx, fS, fwin, fframes;          // stft / istft staging
+    DevBuf status;                         // watchdog word of the strip kernel
+    int last_kernel = 0;                   // 0 generic, 1 strips (introspection)
+    long long tune_smem = 0;               // tuning knobs (lwsb_set_tuning): shared-memory budget, cluster size,
+    int tune_cluster = 0, tune_sweeps = 0; // sweeps per pass; 0 = automatic
+    StripPlan last_plan{};
     std::map<int, DevBuf> twiddles;        // exp(-2 pi i j / N) tables by N
     std::vector<void *> hptr;
 
@@ -171,6 +177,9 @@ extern "C" int lwsb_create(int device, void *stream, lwsb_ctx **out)
     }
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if (const char *e1 = getenv("LWSB_STRIP_SMEM")) c->tune_smem = atoll(e1);
+    if (const char *e2 = getenv("LWSB_STRIP_CLUSTER")) c->tune_cluster = atoi(e2);
+    if (const char *e3 = getenv("LWSB_STRIP_SWEEPS")) c->tune_sweeps = atoi(e3);
     *out = c;
     return LWSB_OK;
 }
@@ -181,7 +190,7 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf *b : {&c->E, &c->A, &c->row_max, &c->leaf_tab, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
-                      &c->drowbase, &c->stage, &c->dptr, &c->dthr, &c->flags, &c->fx, &c->fS, &c->fwin, &c->fframes})
+                      &c->drowbase, &c->stage, &c->dptr, &c->dthr, &c->flags, &c->fx, &c->fS, &c->fwin, &c->fframes, &c->status})
         b->release();
     for (auto &kv : c->twiddles) kv.second.release();
     for (int i = 0; i < 3; ++i) c->raww[i].release();
@@ -282,7 +291,7 @@ extern "C" int lwsb_load(lwsb_ctx *c, const void *const *S_in, const int *T, int
     const int Q = c->w[LWSB_W].Q, L = c->w[LWSB_W].L;
     const int Np = Nreal + 2 * L;
     const int coff = (4 - L % 4) % 4; // bin 0 lands on a 64-byte boundary
-    const int P = (coff + Np + 3) / 4 * 4;
+    const int P = (std::max(coff + Np, strips_min_pitch(Nreal, coff + L)) + 3) / 4 * 4; // strip kernel reads whole blocks
     std::vector<long long> rowbase(B), binbase(B);
     long long rows = 0, bins = 0;
     int maxT = 0;
@@ -374,10 +383,38 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
     if (iterations == 0) return LWSB_OK; // lws.pyx:219-220
     if (int r = use_device(c)) return r;
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
+    const int fold = fold_for(c->Q, flags);
+    StripPlan pl;
+    const bool strips = !(flags & LWSB_FORCE_GENERIC) &&
+                        plan_strips(c->Nreal, c->Q, c->L, iterations, c->maxT, c->B,
+                                    c->tune_smem > 0 ? std::min((size_t)c->tune_smem, c->prop.sharedMemPerBlockOptin)
+                                                     : c->prop.sharedMemPerBlockOptin,
+                                    c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps) &&
+                        c->P >= strips_min_pitch(c->Nreal, c->c0);
+    if (strips) {
+        CU(c, c->status.reserve(sizeof(unsigned)));
+        CU(c, cudaMemsetAsync(c->status.p, 0, sizeof(unsigned), c->stream));
+        if (int r = begin_compute(c)) return r;
+        CU(c, launch_batch_strips(c->view(), c->w[LWSB_W].wr.data(), c->w[LWSB_W].wi.data(), fold,
+                                  c->dthr.as<const double>(), c->max_amp.as<const double>(), iterations, pl,
+                                  c->status.as<unsigned>(), c->stream));
+        c->launches += 1;
+        c->last_kernel = 1; c->last_plan = pl;
+        if (int r = end_compute(c)) return r;
+        unsigned st = 0;
+        CU(c, cudaMemcpyAsync(&st, c->status.p, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (st != 0) {
+            char msg[96];
+            snprintf(msg, sizeof msg, "strip kernel watchdog fired (code 0x%x): results are invalid", st);
+            return fail(c, LWSB_ERR_CUDA, msg);
+        }
+        return LWSB_OK;
+    }
     if (int r = begin_compute(c)) return r;
-    launch_sweeps_generic(c->view(), c->devw(LWSB_W), fold_for(c->Q, flags), c->Q, 1, c->dthr.as<const double>(),
-                          iterations, c->stream);
+    launch_sweeps_generic(c->view(), c->devw(LWSB_W), fold, c->Q, 1, c->dthr.as<const double>(), iterations, c->stream);
     c->launches += 1;
+    c->last_kernel = 0;
     return end_compute(c);
 }
 
@@ -629,6 +666,25 @@ extern "C" int lwsb_last_compute_ms(lwsb_ctx *c, float *ms)
 
 extern "C" long long lwsb_launch_count(const lwsb_ctx *c) { return c ? c->launches : 0; }
 
+extern "C" int lwsb_set_tuning(lwsb_ctx *c, long long smem_limit, int cluster, int sweeps_per_pass)
+{
+    CHECK_CTX(c);
+    if (smem_limit < 0 || cluster < 0 || cluster > 8 || (cluster & (cluster - 1)) || sweeps_per_pass < 0)
+        return fail(c, LWSB_ERR_ARG, "bad tuning values");
+    c->tune_smem = smem_limit; c->tune_cluster = cluster; c->tune_sweeps = sweeps_per_pass;
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_last_batch_plan(const lwsb_ctx *c, int *out9)
+{
+    if (!c || !out9) return LWSB_ERR_ARG;
+    if (c->last_kernel != 1) return 0;
+    const StripPlan &p = c->last_plan;
+    const int v[9] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes};
+    for (int i = 0; i < 9; ++i) out9[i] = v[i];
+    return 1;
+}
+
 extern "C" int lwsb_device_info(lwsb_ctx *c, int *sm_count, int *cc_major, int *cc_minor, long long *hbm_bytes)
 {
     CHECK_CTX(c);
@@ -670,6 +726,17 @@ extern "C" int lwsb_debug_terms(const double *wr, const double *wi, int Q, int L
         if (ci) ci[i] = t[i].ci;
     }
     return cnt;
+}
+
+extern "C" int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, int maxT, int B, long long smem_limit,
+                                      int sm_count, int force_cluster, int max_sweeps, int *out9)
+{
+    if (!out9) return LWSB_ERR_ARG;
+    StripPlan p;
+    if (!plan_strips(Nreal, Q, L, iterations, maxT, B, (size_t)smem_limit, sm_count, &p, force_cluster, max_sweeps)) return 0;
+    const int v[9] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes};
+    for (int i = 0; i < 9; ++i) out9[i] = v[i];
+    return 1;
 }
 
 extern "C" long long lwsb_debug_online_chain_length(int T, int iterations, int look_ahead)

@@ -27,6 +27,17 @@ void launch_online_generic(const LwsbView &v, const LwsbW *w3, int fold, const d
                            cudaStream_t s);
 void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, int iters, cudaStream_t s);
 
+// kernels_batch.cu
+struct StripPlan {
+    int C, NBr, NBV, NS, G, R, pitch, nthreads, smem_bytes;
+};
+bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
+                 int force_cluster = 0, int max_sweeps = 0);
+int strips_min_pitch(int Nreal, int c0);
+cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const double *wi_host, int fold,
+                                const double *thr, const double *max_amp, int iters, const StripPlan &pl,
+                                unsigned *status, cudaStream_t s);
+
 // kernels_fft.cu
 cudaError_t launch_stft(const double *x, int B, int nsamples, const double *awin, int fsize, int hop, int N, int logN,
                         int pre, const double2 *tw, double2 *S, int M, cudaStream_t s);

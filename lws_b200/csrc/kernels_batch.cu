@@ -1,0 +1,566 @@
+// kernels_batch.cu -- the tuned batch_lws kernel: column strips on a thread-block cluster.
+//
+// Work decomposition (DESIGN.md has the derivation and the dependency proofs)
+//   * One CLUSTER of C CTAs per utterance; CTA c ("strip c") owns the bins [c*W, (c+1)*W),
+//     W = 8*NBr, of EVERY frame and streams the frames through a ring of R rows in its own
+//     shared memory (row = W + 2L complex128: own bins plus an L-bin halo on either side).
+//     Rows enter by TMA bulk copies (cp.async.bulk, mbarrier-signalled) LEAD frames ahead of
+//     their first use and leave by TMA bulk stores when their last sweep of the pass is done.
+//   * Bins are processed in BLOCKS of 8 consecutive bins ("macro-step").  Within a strip the
+//     thread of frame m runs 2 blocks behind the thread of frame m-1 (the stencil reaches
+//     5 bins, i.e. into the next block, so 2 blocks is the smallest safe lag) and sweep g+1
+//     runs Q frames behind sweep g: thread (j, g), j in [0, NS), g in [0, G), handles block
+//     xb = (t - 2j) mod NBV of frame  j + NS*floor((t - 2j)/NBV) - Q*g  at macro-step t.
+//     All of this is the reference's raster order relaxed only where the data dependences
+//     allow it, so every bin sees exactly the neighbour values the sequential code sees.
+//   * G sweeps are in flight per pass (as many as the ring has room for); a call of `iters`
+//     sweeps takes ceil(active/G) passes over the utterance, where sweeps whose threshold is
+//     not below max|S| are dropped up front (they cannot move any bin).
+//   * Strips run in lock step, NBr macro-steps apart (strip c+1 behind strip c).  A bin block
+//     on a strip edge is written into the neighbour's halo through distributed shared memory;
+//     after every macro-step the control warp publishes the strip's progress to both
+//     neighbours (st.release.cluster) and polls theirs (ld.acquire.cluster) while the compute
+//     warps work on the next macro-step.
+//   * Arithmetic is the reference's, operation for operation (exact.cuh): results are
+//     bit-identical to lwslib's LWSQ2 / LWSQ4 / LWSanyQ.
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <type_traits>
+#include "exact.cuh"
+#include "kernels.h"
+#include "lwsb_common.h"
+
+namespace cg = cooperative_groups;
+
+namespace lwsb {
+
+namespace {
+
+constexpr int SL = 5;          // stencil reach in bins this kernel is specialised for (L)
+constexpr int SBK = 8;         // bins per block
+constexpr int SLEAD = 2;       // frames of TMA look-ahead
+constexpr unsigned SPIN_LIMIT = 1u << 24;
+
+template <int Q>
+struct StripW {                // one weight set, reference layout, in the kernel parameter bank
+    double wr[Q][Q][SL + 1];
+    double wi[Q][Q][SL + 1];
+    unsigned flag[Q][Q];       // bit k: |W[p][r][k]| > 1e-12
+    int fold;                  // LWSB_FOLD_*
+};
+
+struct StripParams {
+    LwsbView v;
+    const double *thr;         // [iters] unscaled thresholds
+    const double *max_amp;     // [B]
+    int iters;
+    int C, NBr, NBV, NS, G, R, pitch;
+    unsigned *status;          // [0]: 0 ok, else first watchdog code
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t *bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// global -> shared bulk copy (TMA), completion counted in bytes on an mbarrier of this CTA
+__device__ __forceinline__ void tma_load_row(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (TMA), tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void tma_store_row(void *dst, const void *src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned ld_acquire_cluster(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.cluster.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cluster(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// CTA-wide barrier usable from the role-split (control / compute) code paths
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1;" ::: "memory"); }
+
+__device__ __forceinline__ void watchdog(unsigned *status, unsigned code) { atomicCAS(status, 0u, code); }
+
+// ---------------------------------------------------------------- one block of 8 bins
+// Accessor over the shared-memory ring: rowoff[dr + Q - 1] is the byte offset of ring row
+// (frame + dr) and `col` the ring column of the bin being updated.
+template <int Q>
+struct RingCell {
+    const unsigned char *ring;
+    unsigned rowoff[2 * Q - 1];
+    int col;
+    __device__ __forceinline__ double2 operator()(int dr, int dk) const
+    {
+        return *reinterpret_cast<const double2 *>(ring + rowoff[dr + Q - 1] + (unsigned)(col + dk) * 16u);
+    }
+};
+
+// the reference's weighted sum with everything but the data resolved at compile time:
+// P = bin mod Q, weights / flags straight from the parameter bank
+template <int Q, int P, int FOLD>
+__device__ __forceinline__ void strip_weighted_sum(const RingCell<Q> &E, const StripW<Q> &w, double &tr, double &ti)
+{
+    constexpr int PN = (Q - P) % Q;
+    tr = 0.0; ti = 0.0;
+    // centre frame, bins n -+ k (lwslib.cpp:88-101, 169-182, 299-312)
+#pragma unroll
+    for (int k = 1; k <= SL; ++k)
+        if (w.flag[P][0] & (1u << k)) {
+            const double2 b = E(0, -k), c = E(0, +k);
+            x_pair(tr, ti, w.wr[P][0][k], w.wi[P][0][k], b.x, b.y, c.x, c.y);
+        }
+    auto both = [&](auto rc, auto minusc) {
+        constexpr int r = decltype(rc)::value;
+        constexpr bool minus = decltype(minusc)::value;
+        if (w.flag[P][r] & 1u) {
+            const double2 b = E(-r, 0), c = E(+r, 0);
+            x_pair(tr, ti, w.wr[P][r][0], w.wi[P][r][0], b.x, b.y, c.x, c.y);
+        }
+#pragma unroll
+        for (int k = 1; k <= SL; ++k) {
+            if (FOLD == LWSB_FOLD_ANY) {
+                if (w.flag[P][r] & (1u << k)) {
+                    const double2 b = E(-r, -k), c = E(+r, -k);
+                    x_pair(tr, ti, w.wr[P][r][k], w.wi[P][r][k], b.x, b.y, c.x, c.y);
+                }
+                if (w.flag[PN][r] & (1u << k)) {
+                    const double2 b = E(+r, +k), c = E(-r, +k);
+                    x_pair(tr, ti, w.wr[PN][r][k], w.wi[PN][r][k], b.x, b.y, c.x, c.y);
+                }
+            } else if (w.flag[P][r] & (1u << k)) {
+                const double2 e1 = E(-r, -k), e2 = E(+r, +k), e3 = E(+r, -k), e4 = E(-r, +k);
+                double br, bi, cr, ci;
+                if (minus) {
+                    br = __dsub_rn(e1.x, e2.x); bi = __dsub_rn(e1.y, e2.y);
+                    cr = __dsub_rn(e3.x, e4.x); ci = __dsub_rn(e3.y, e4.y);
+                } else {
+                    br = __dadd_rn(e1.x, e2.x); bi = __dadd_rn(e1.y, e2.y);
+                    cr = __dadd_rn(e3.x, e4.x); ci = __dadd_rn(e3.y, e4.y);
+                }
+                x_pair(tr, ti, w.wr[P][r][k], w.wi[P][r][k], br, bi, cr, ci);
+            }
+        }
+    };
+    using T_ = std::true_type;
+    using F_ = std::false_type;
+    if constexpr (FOLD == LWSB_FOLD_Q4 && (P & 1)) {
+        // odd bins: r = 1, 3 with the sign-flipped folding, then r = 2 (lwslib.cpp:186-235)
+        static_assert(FOLD != LWSB_FOLD_Q4 || Q == 4, "the Q4 folding is defined for Q = 4");
+        both(std::integral_constant<int, 1>{}, T_{});
+        both(std::integral_constant<int, 3>{}, T_{});
+        both(std::integral_constant<int, 2>{}, F_{});
+    } else {
+        if constexpr (Q > 1) both(std::integral_constant<int, 1>{}, F_{});
+        if constexpr (Q > 2) both(std::integral_constant<int, 2>{}, F_{});
+        if constexpr (Q > 3) both(std::integral_constant<int, 3>{}, F_{});
+        if constexpr (Q > 4) both(std::integral_constant<int, 4>{}, F_{});
+        if constexpr (Q > 5) both(std::integral_constant<int, 5>{}, F_{});
+        if constexpr (Q > 6) both(std::integral_constant<int, 6>{}, F_{});
+        if constexpr (Q > 7) both(std::integral_constant<int, 7>{}, F_{});
+    }
+}
+
+struct BlockCtx {
+    unsigned char *ring;        // this CTA's ring
+    unsigned char *ring_left;   // left / right neighbour's ring through DSMEM (nullptr at the ends)
+    unsigned char *ring_right;
+    unsigned ownoff;            // byte offset of the frame's ring row
+    int xb;                     // block index inside the strip
+    int n0;                     // first bin of the block (global bin index)
+    int b0;                     // first bin of the strip
+    int Nreal, NBr;
+    bool first_strip;
+};
+
+template <int Q, int P, int FOLD>
+__device__ __forceinline__ void strip_update_bin(RingCell<Q> &cell, const StripW<Q> &w, const BlockCtx &bc, int i, double a)
+{
+    cell.col = SL + SBK * bc.xb + i;
+    double tr, ti;
+    strip_weighted_sum<Q, P, FOLD>(cell, w, tr, ti);
+    double2 val;
+    if (!x_project(tr, ti, a, val)) return;
+    const int n = bc.n0 + i;
+    double2 *own = reinterpret_cast<double2 *>(bc.ring + bc.ownoff);
+    own[cell.col] = val;
+    const double2 cj = make_double2(val.x, -val.y);
+    // mirrored copies, refreshed at once (lwslib.cpp:362-368); ring column of bin q is SL + q - b0
+    if (n >= 1 && n <= SL) { if (bc.first_strip) own[SL - n] = cj; }
+    else if (n >= bc.Nreal - 1 - SL && n <= bc.Nreal - 2) own[SL + 2 * (bc.Nreal - 1) - n - bc.b0] = cj;
+    // halo copies in the neighbouring strips (distributed shared memory)
+    if (bc.xb == 0 && i < SL && bc.ring_left)
+        reinterpret_cast<double2 *>(bc.ring_left + bc.ownoff)[SL + SBK * bc.NBr + i] = val;
+    if (bc.xb == bc.NBr - 1 && i >= SBK - SL && bc.ring_right)
+        reinterpret_cast<double2 *>(bc.ring_right + bc.ownoff)[i - (SBK - SL)] = val;
+}
+
+template <int Q, int FOLD, int I>
+__device__ __forceinline__ void strip_update_block(RingCell<Q> &cell, const StripW<Q> &w, const BlockCtx &bc,
+                                                   const double *amp, unsigned active)
+{
+    // bins of a block in order; the block starts at a multiple of 8 bins, so bin I has residue I mod Q
+    if constexpr (I < SBK) {
+        if (active & (1u << I)) strip_update_bin<Q, I % Q, FOLD>(cell, w, bc, I, amp[I]);
+        strip_update_block<Q, FOLD, I + 1>(cell, w, bc, amp, active);
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int Q, int FOLD>
+__global__ void __launch_bounds__(320, 1)
+k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ StripW<Q> w)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = prm.C;
+    const int c = (int)cluster.block_rank();
+    const int cid = blockIdx.x / C, ncl = gridDim.x / C;
+    const int tid = threadIdx.x;
+    const int nct = (int)blockDim.x - 32; // compute threads; the last warp is the control warp
+    const bool is_ctrl = tid >= nct;
+    const int lane = tid & 31;
+    const LwsbView &v = prm.v;
+    const int NBr = prm.NBr, NBV = prm.NBV, NS = prm.NS, G = prm.G, R = prm.R, pitch = prm.pitch;
+    const int Nreal = v.Nreal, P = v.P;
+    const unsigned rowbytes = (unsigned)pitch * 16u;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *ring = smem;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + (size_t)R * rowbytes);
+    unsigned *flags = reinterpret_cast<unsigned *>(mbar + R); // [0]: progress of the left neighbour, [1]: of the right one
+    int *nact = reinterpret_cast<int *>(flags + 4);
+    int *act = nact + 4;                                      // indices of the sweeps that can move a bin
+
+    unsigned char *ring_left = c > 0 ? reinterpret_cast<unsigned char *>(cluster.map_shared_rank(ring, c - 1)) : nullptr;
+    unsigned char *ring_right = c < C - 1 ? reinterpret_cast<unsigned char *>(cluster.map_shared_rank(ring, c + 1)) : nullptr;
+    unsigned *flag_at_left = c > 0 ? cluster.map_shared_rank(flags, c - 1) + 1 : nullptr;       // I am its right neighbour
+    unsigned *flag_at_right = c < C - 1 ? cluster.map_shared_rank(flags, c + 1) + 0 : nullptr;  // I am its left neighbour
+
+    const int b0 = c * NBr * SBK;                                     // first bin of the strip
+    int nb_my = (Nreal - b0 + SBK - 1) / SBK;                         // blocks holding real bins
+    nb_my = nb_my < 0 ? 0 : (nb_my > NBr ? NBr : nb_my);
+    const int gcol0 = v.c0 + b0 - SL;                                 // global column of ring column 0
+    const unsigned load_bytes = (unsigned)(SBK * NBr + 2 * SL) * 16u; // a full ring row
+    const int wb_lo = c == 0 ? 0 : SL;                                // ring columns written back (mirrors included at the ends)
+    const int wb_hi = c == C - 1 ? SL + (Nreal - b0) + SL : SL + SBK * NBr;
+
+    // per-thread slot: frame residue j, sweep slot g
+    const int j = tid % NS, g = tid / NS;
+    const bool has_slot = !is_ctrl && g < G;
+
+    bool mbar_live = false;
+    for (int u = cid; u < v.B; u += ncl) {
+        const int T = v.T[u];
+        const int Tp = T + 2 * (Q - 1);
+        const long long grow0 = v.rowbase[u];
+        const double mean = v.mean_amp[u];
+        __syncthreads();
+        if (tid == 0) {
+            const double mx = prm.max_amp[u];
+            int n = 0;
+            for (int i = 0; i < prm.iters; ++i)
+                if (__dmul_rn(prm.thr[i], mean) < mx) act[n++] = i; // a sweep with threshold >= max|S| moves nothing
+            *nact = n;
+        }
+        __syncthreads();
+        const int n_act = *nact;
+        const int npass = (n_act + G - 1) / G;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int Gp = min(G, n_act - pass * G);
+            const int nsteps = 2 * (T - 1 + Q * (Gp - 1)) + NBV;
+            const double thr = (has_slot && g < Gp) ? __dmul_rn(prm.thr[act[pass * G + g]], mean) : 0.0; // lws.pyx:245
+
+            // ---- pass prologue: previous pass fully written back everywhere, ring (re)initialised
+            if (is_ctrl && lane == 0) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
+            cluster.sync();
+            if (is_ctrl && lane == 0) {
+                for (int s = 0; s < R; ++s) {
+                    if (mbar_live) mbar_inval(&mbar[s]);
+                    mbar_init(&mbar[s], 1);
+                }
+                mbar_live = true;
+                flags[0] = 0; flags[1] = 0;
+                fence_mbar_init();
+                fence_proxy_async();
+                const int npre = min(Tp, 2 * (Q - 1) + SLEAD + 1);
+                for (int e = 0; e < npre; ++e) {
+                    mbar_expect_tx(&mbar[e % R], load_bytes);
+                    tma_load_row(ring + (size_t)(e % R) * rowbytes, v.E + (grow0 + e) * P + gcol0, load_bytes, &mbar[e % R]);
+                }
+            }
+            cluster.sync();
+
+            if (is_ctrl) {
+                // ================= control warp: neighbour hand-shake, TMA traffic =================
+                auto poll = [&](int t) { // conditions for macro-step t (DESIGN.md "strip hand-shake")
+                    if (lane != 0) return;
+                    if (c > 0) {
+                        const unsigned need = (unsigned)min(t + NBr, nsteps);
+                        unsigned spins = 0;
+                        while (ld_acquire_cluster(&flags[0]) < need)
+                            if (++spins > SPIN_LIMIT) { watchdog(prm.status, 0x100u + c); break; }
+                    }
+                    if (c < C - 1 && t - NBr > 0) {
+                        const unsigned need = (unsigned)(t - NBr);
+                        unsigned spins = 0;
+                        while (ld_acquire_cluster(&flags[1]) < need)
+                            if (++spins > SPIN_LIMIT) { watchdog(prm.status, 0x200u + c); break; }
+                    }
+                };
+                poll(0);
+                cta_sync(); // releases the compute warps into macro-step 0
+                for (int t = 0; t < nsteps; ++t) {
+                    if (t + 1 < nsteps) poll(t + 1);
+                    cta_sync(); // macro-step t computed by every thread of the strip
+                    if (lane == 0) {
+                        const unsigned done = (unsigned)(t + 1);
+                        if (flag_at_left) st_release_cluster(flag_at_left, done);
+                        if (flag_at_right) st_release_cluster(flag_at_right, done);
+                        // frame whose last sweep of this pass finished its last real block in step t
+                        const int tf = t - (nb_my - 1);
+                        if (nb_my > 0 && tf >= 0 && (tf & 1) == 0) {
+                            const int m = tf / 2 - Q * (Gp - 1);
+                            if (m >= 0 && m < T) {
+                                const int e = m + Q - 1;
+                                fence_proxy_async();
+                                tma_store_row(v.E + (grow0 + e) * P + gcol0 + wb_lo,
+                                              ring + (size_t)(e % R) * rowbytes + (size_t)wb_lo * 16u, (unsigned)(wb_hi - wb_lo) * 16u);
+                            }
+                        }
+                        // next frame into the slot freed longest ago
+                        if (((t + 1) & 1) == 0) {
+                            const int e = (t + 1) / 2 + 2 * (Q - 1) + SLEAD;
+                            if (e < Tp) {
+                                tma_store_wait_read();
+                                fence_proxy_async();
+                                mbar_expect_tx(&mbar[e % R], load_bytes);
+                                tma_load_row(ring + (size_t)(e % R) * rowbytes, v.E + (grow0 + e) * P + gcol0, load_bytes, &mbar[e % R]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // ================= compute warps =================
+                int xb = -2 * j;          // block index; negative while the slot has not started
+                int m = j - Q * g;        // frame of the slot
+                cta_sync();               // control warp has verified macro-step 0
+                for (int t = 0; t < nsteps; ++t) {
+                    if ((t & 1) == 0) {
+                        // rows entering use at this frame clock must have landed
+                        const int k = t >> 1;
+                        const int e_lo = k == 0 ? 0 : k + 2 * (Q - 1), e_hi = k + 2 * (Q - 1);
+                        for (int e = e_lo; e <= e_hi && e < Tp; ++e) {
+                            unsigned spins = 0;
+                            while (!mbar_try_wait(&mbar[e % R], (unsigned)((e / R) & 1)))
+                                if (++spins > SPIN_LIMIT) { watchdog(prm.status, 0x300u + c); break; }
+                        }
+                    }
+                    if (has_slot && g < Gp && xb >= 0 && xb < nb_my && m >= 0 && m < T) {
+                        const int e = m + Q - 1;
+                        const int n0 = b0 + SBK * xb;
+                        // amplitudes of the block (row-major plane in global memory, read-only)
+                        const double2 *ap = reinterpret_cast<const double2 *>(v.A + (grow0 + e) * P + v.c0 + n0);
+                        double amp[SBK];
+                        unsigned active = 0;
+#pragma unroll
+                        for (int q = 0; q < SBK / 2; ++q) {
+                            const double2 a2 = __ldg(ap + q);
+                            amp[2 * q] = a2.x; amp[2 * q + 1] = a2.y;
+                        }
+#pragma unroll
+                        for (int i = 0; i < SBK; ++i)
+                            if (n0 + i < Nreal && amp[i] > thr) active |= 1u << i; // lwslib.cpp:295-296
+                        if (active) {
+                            RingCell<Q> cell;
+                            cell.ring = ring;
+                            const int es = e % R;
+#pragma unroll
+                            for (int d = 0; d < 2 * Q - 1; ++d) {
+                                int s = es + d - (Q - 1);
+                                s = s < 0 ? s + R : (s >= R ? s - R : s);
+                                cell.rowoff[d] = (unsigned)s * rowbytes;
+                            }
+                            BlockCtx bc;
+                            bc.ring = ring; bc.ring_left = ring_left; bc.ring_right = ring_right;
+                            bc.ownoff = cell.rowoff[Q - 1]; bc.xb = xb; bc.n0 = n0; bc.b0 = b0;
+                            bc.Nreal = Nreal; bc.NBr = NBr; bc.first_strip = (c == 0);
+                            strip_update_block<Q, FOLD, 0>(cell, w, bc, amp, active);
+                        }
+                    }
+                    cta_sync();
+                    if (++xb == NBV) { xb = 0; m += NS; }
+                }
+            }
+        }
+        // ---- utterance epilogue: everything written back before the ring is reused
+        if (is_ctrl && lane == 0) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
+    }
+    cluster.sync(); // no CTA leaves while a neighbour may still address its shared memory
+}
+
+} // namespace
+
+// ---------------------------------------------------------------- host side
+namespace {
+
+template <int Q, int FOLD>
+cudaError_t launch_strips_t(const StripParams &prm, const StripW<Q> &w, const StripPlan &pl, int B, cudaStream_t s)
+{
+    auto kern = k_batch_strips<Q, FOLD>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (pl.C > 8) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(pl.nthreads);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(pl.C); // placeholder for the occupancy query
+    int ncl = 0;
+    e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+    if (e != cudaSuccess) return e;
+    if (ncl < 1) return cudaErrorLaunchOutOfResources;
+    cfg.gridDim = dim3((unsigned)(std::min(ncl, B) * pl.C));
+    return cudaLaunchKernelEx(&cfg, kern, prm, w);
+}
+
+template <int Q>
+cudaError_t launch_strips_q(const StripParams &prm, const double *wr, const double *wi, int fold, const StripPlan &pl,
+                            int B, cudaStream_t s)
+{
+    StripW<Q> w;
+    for (int p = 0; p < Q; ++p)
+        for (int r = 0; r < Q; ++r) {
+            unsigned f = 0;
+            for (int k = 0; k <= SL; ++k) {
+                const size_t i = ((size_t)p * Q + r) * (SL + 1) + k;
+                w.wr[p][r][k] = wr[i]; w.wi[p][r][k] = wi[i];
+                if (std::hypot(wr[i], wi[i]) > 1.0e-12) f |= 1u << k; // lws.pyx:231-232
+            }
+            w.flag[p][r] = f;
+        }
+    w.fold = fold;
+    if (fold == LWSB_FOLD_ANY) return launch_strips_t<Q, LWSB_FOLD_ANY>(prm, w, pl, B, s);
+    if constexpr (Q == 4) { if (fold == LWSB_FOLD_Q4) return launch_strips_t<4, LWSB_FOLD_Q4>(prm, w, pl, B, s); }
+    if constexpr (Q == 2) { if (fold == LWSB_FOLD_Q2) return launch_strips_t<2, LWSB_FOLD_Q2>(prm, w, pl, B, s); }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace
+
+// Chooses cluster size, strip width and sweeps per pass.  Returns false when the shape is not
+// served by this kernel (the generic kernel takes over).
+bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
+                 int force_cluster, int max_sweeps)
+{
+    if (L != SL || !(Q == 2 || Q == 4 || Q == 8) || iters < 1) return false;
+    const int nbt = (Nreal + SBK - 1) / SBK; // blocks holding real bins
+    bool found = false;
+    double best = 0.0;
+    for (int C = 1; C <= 8; C *= 2) {
+        if (force_cluster > 0 && C != force_cluster) continue;
+        const int NBr = (nbt + C - 1) / C;
+        const int NBV = NBr + (NBr & 1);
+        const int NS = NBV / 2;
+        if (NBr < 2) continue;
+        // every strip needs real bins and the last one the whole upper mirror zone
+        if ((C - 1) * NBr * SBK > Nreal - 1 - SL) continue;
+        int pitch = SBK * NBr + 2 * SL;
+        if ((pitch & 1) == 0) ++pitch; // odd pitch: conflict-free 128-bit accesses across a warp's rows
+        const size_t rowbytes = (size_t)pitch * 16;
+        const size_t fixed = 64 + 16 + (size_t)(iters + 8) * sizeof(int) + 256;
+        if (smem_limit < fixed + rowbytes * 8) continue;
+        const int Rmax = (int)((smem_limit - fixed) / (rowbytes + 8));
+        int G = (Rmax - (Q - 1) - SLEAD - NS - 1) / Q;
+        G = std::min(G, (320 - 32) / NS);
+        G = std::min(G, iters);
+        if (max_sweeps > 0) G = std::min(G, max_sweeps);
+        if (G < 1) continue;
+        const int npass = (iters + G - 1) / G;
+        G = (iters + npass - 1) / npass; // same number of passes, evenly filled
+        const int R = Q * G + Q + SLEAD + NS;
+        const int ncl = std::max(1, (sm_count * 9 / 10) / C); // GPC packing loses a few SMs to clusters
+        const double rounds = std::ceil((double)B / ncl);
+        const double steps = 2.0 * (maxT + Q * G) + NBV + (C - 1) * NBr;
+        const double cost = rounds * npass * steps * (std::max(NS * G, 64) + 24.0);
+        if (!found || cost < best) {
+            found = true; best = cost;
+            out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->R = R; out->pitch = pitch;
+            out->nthreads = (NS * G + 31) / 32 * 32 + 32;
+            out->smem_bytes = (int)(fixed + (size_t)R * (rowbytes + 8));
+        }
+    }
+    return found;
+}
+
+int strips_min_pitch(int Nreal, int c0)
+{
+    // the widest plan reads up to 8 blocks past the last real block plus the right halo
+    return c0 + ((Nreal + SBK - 1) / SBK + 8) * SBK + SL;
+}
+
+cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const double *wi_host, int fold,
+                                const double *thr, const double *max_amp, int iters, const StripPlan &pl,
+                                unsigned *status, cudaStream_t s)
+{
+    StripParams prm;
+    prm.v = v; prm.thr = thr; prm.max_amp = max_amp; prm.iters = iters;
+    prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch;
+    prm.status = status;
+    switch (v.Q) {
+    case 2: return launch_strips_q<2>(prm, wr_host, wi_host, fold, pl, v.B, s);
+    case 4: return launch_strips_q<4>(prm, wr_host, wi_host, fold, pl, v.B, s);
+    case 8: return launch_strips_q<8>(prm, wr_host, wi_host, fold, pl, v.B, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace lwsb
