@@ -42,7 +42,7 @@ namespace {
 constexpr int SL = 5;          // stencil reach in bins this kernel is specialised for (L)
 constexpr int SBK = 8;         // bins per block
 constexpr int SLEAD = 2;       // frames of TMA look-ahead
-constexpr unsigned SPIN_LIMIT = 1u << 24;
+constexpr unsigned SPIN_LIMIT = 1u << 22; // polls before a wait is declared dead (~0.5 s)
 
 template <int Q>
 struct StripW {                // one weight set, reference layout, in the kernel parameter bank
@@ -71,6 +71,10 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 __device__ __forceinline__ void mbar_inval(uint64_t *bar)
 {
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
 {
@@ -121,7 +125,16 @@ __device__ __forceinline__ void st_release_cluster(unsigned *p, unsigned v)
 // CTA-wide barrier usable from the role-split (control / compute) code paths
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1;" ::: "memory"); }
 
-__device__ __forceinline__ void watchdog(unsigned *status, unsigned code) { atomicCAS(status, 0u, code); }
+// Bounded waiting: a protocol error must end the kernel, not hang the GPU.  Returns false when
+// the wait has to be abandoned (this or another CTA recorded a time-out in *status).
+__device__ __forceinline__ bool keep_waiting(unsigned &spins, unsigned *status, unsigned code)
+{
+    if ((++spins & 1023u) == 0) {
+        if (*reinterpret_cast<volatile unsigned *>(status) != 0u) return false;
+        if (spins > SPIN_LIMIT) { atomicCAS(status, 0u, code); return false; }
+    }
+    return true;
+}
 
 // ---------------------------------------------------------------- one block of 8 bins
 // Accessor over the shared-memory ring: rowoff[dr + Q - 1] is the byte offset of ring row
@@ -315,13 +328,12 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
             if (is_ctrl && lane == 0) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
             cluster.sync();
             if (is_ctrl && lane == 0) {
-                for (int s = 0; s < R; ++s) {
-                    if (mbar_live) mbar_inval(&mbar[s]);
-                    mbar_init(&mbar[s], 1);
+                if (!mbar_live) {
+                    for (int s = 0; s < R; ++s) mbar_init(&mbar[s], 1);
+                    fence_mbar_init();
+                    mbar_live = true;
                 }
-                mbar_live = true;
                 flags[0] = 0; flags[1] = 0;
-                fence_mbar_init();
                 fence_proxy_async();
                 const int npre = min(Tp, 2 * (Q - 1) + SLEAD + 1);
                 for (int e = 0; e < npre; ++e) {
@@ -339,21 +351,23 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                         const unsigned need = (unsigned)min(t + NBr, nsteps);
                         unsigned spins = 0;
                         while (ld_acquire_cluster(&flags[0]) < need)
-                            if (++spins > SPIN_LIMIT) { watchdog(prm.status, 0x100u + c); break; }
+                            if (!keep_waiting(spins, prm.status, 0x10000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
                     }
                     if (c < C - 1 && t - NBr > 0) {
                         const unsigned need = (unsigned)(t - NBr);
                         unsigned spins = 0;
                         while (ld_acquire_cluster(&flags[1]) < need)
-                            if (++spins > SPIN_LIMIT) { watchdog(prm.status, 0x200u + c); break; }
+                            if (!keep_waiting(spins, prm.status, 0x20000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
                     }
                 };
                 poll(0);
                 cta_sync(); // releases the compute warps into macro-step 0
                 for (int t = 0; t < nsteps; ++t) {
-                    if (t + 1 < nsteps) poll(t + 1);
                     cta_sync(); // macro-step t computed by every thread of the strip
                     if (lane == 0) {
+                        // publish first: the neighbours' next macro-step waits for this one.  (Polling for
+                        // step t+1 before publishing step t would dead-lock: in lock step the neighbour's
+                        // matching step finishes only after it has seen this strip's step t.)
                         const unsigned done = (unsigned)(t + 1);
                         if (flag_at_left) st_release_cluster(flag_at_left, done);
                         if (flag_at_right) st_release_cluster(flag_at_right, done);
@@ -379,8 +393,16 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                             }
                         }
                     }
+                    if (t + 1 < nsteps) poll(t + 1);
                     __syncwarp();
+                    cta_sync(); // releases the compute warps into macro-step t + 1
                 }
+                // Slot s received Tp/R (+1) rows in this pass, one mbarrier phase each.  The waits address
+                // phases by parity counted from the start of the pass, so slots that saw an odd number of
+                // phases get one empty phase: every barrier starts the next pass at parity 0 again.
+                if (lane == 0)
+                    for (int s = 0; s < R; ++s)
+                        if ((Tp / R + (s < Tp % R ? 1 : 0)) & 1) mbar_arrive(&mbar[s]);
             } else {
                 // ================= compute warps =================
                 int xb = -2 * j;          // block index; negative while the slot has not started
@@ -394,7 +416,7 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                         for (int e = e_lo; e <= e_hi && e < Tp; ++e) {
                             unsigned spins = 0;
                             while (!mbar_try_wait(&mbar[e % R], (unsigned)((e / R) & 1)))
-                                if (++spins > SPIN_LIMIT) { watchdog(prm.status, 0x300u + c); break; }
+                                if (!keep_waiting(spins, prm.status, 0x30000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
                         }
                     }
                     if (has_slot && g < Gp && xb >= 0 && xb < nb_my && m >= 0 && m < T) {
@@ -429,8 +451,9 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                             strip_update_block<Q, FOLD, 0>(cell, w, bc, amp, active);
                         }
                     }
-                    cta_sync();
+                    cta_sync(); // macro-step t done
                     if (++xb == NBV) { xb = 0; m += NS; }
+                    cta_sync(); // neighbours ready for macro-step t + 1
                 }
             }
         }

@@ -225,3 +225,66 @@ def test_no_fallback_and_launch_counter(gpu):
     assert ctx.launch_count() - n0 >= 3  # extend + stats, sweeps, crop
     assert ctx.last_compute_ms() > 0.0
     ctx.close()
+
+
+# ------------------------------------------------------------------ cluster strip kernel
+STRIP_CASES = [  # fsize, hop, samples, iterations, cluster, sweeps per pass, smem budget
+    (512, 128, 6000, 6, 1, 0, 0), (512, 128, 6000, 6, 2, 0, 0), (512, 128, 6000, 6, 4, 0, 0),
+    (512, 128, 6000, 7, 2, 3, 0), (512, 128, 6000, 7, 4, 2, 60000), (512, 128, 700, 5, 2, 2, 0),
+    (1024, 256, 30000, 12, 2, 0, 0), (1024, 256, 30000, 12, 4, 0, 0), (1024, 256, 30000, 12, 8, 0, 0),
+    (1024, 256, 30000, 9, 8, 2, 0), (2048, 256, 40000, 8, 4, 0, 0), (2048, 256, 40000, 8, 8, 0, 0),
+    (128, 64, 9000, 10, 1, 0, 0), (128, 64, 9000, 10, 2, 3, 0), (512, 128, 32000, 100, 0, 0, 0),
+]
+
+
+@pytest.mark.parametrize("fs,hop,n,its,cluster,sweeps,smem", STRIP_CASES,
+                         ids=["%d-%d-n%d-it%d-C%d-G%d-S%d" % c for c in STRIP_CASES])
+def test_strip_kernel_bit_exact(gpu, oracle, fs, hop, n, its, cluster, sweeps, smem):
+    """The cluster strip kernel (TMA ring, DSMEM halos) over cluster sizes, pass counts and ring
+    sizes: identical bits to the oracle, and the plan asked for is the plan that ran."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(fs, hop), gpu.lws(fs, hop)
+    A = np.abs(po.stft(make_signal("tonal", 3, n)))
+    try:
+        ctx.set_tuning(smem, cluster, sweeps)
+        for thr in (np.zeros(its), gpu.get_thresholds(its, 100 if its > 50 else 2.0, 0.1, 1)):
+            Y = pg.batch_lws(A, thresholds=thr)
+            plan = ctx.last_batch_plan()
+            assert plan is not None, "strip kernel did not run"
+            if cluster:
+                assert plan["cluster"] == cluster
+            if sweeps:
+                assert plan["sweeps_per_pass"] <= sweeps
+            _close(Y, po.batch_lws(A, thresholds=thr), "strips %s" % (plan,))
+    finally:
+        ctx.set_tuning(0, 0, 0)
+
+
+def test_strip_kernel_ragged_batch_persistent_clusters(gpu, oracle):
+    """More utterances than resident clusters, different lengths: the persistent cluster loop."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(512, 128), gpu.lws(512, 128)
+    As = [np.abs(po.stft(make_signal("white" if i % 2 else "tonal", 50 + i, 3000 + 700 * (i % 9)))) for i in range(45)]
+    thr = gpu.get_thresholds(9, 2.0, 0.2, 1)
+    want = [po.batch_lws(A, thresholds=thr) for A in As]
+    try:
+        for cl in (4, 2, 0):
+            ctx.set_tuning(0, cl, 0)
+            Ys = pg.batch_lws(As, thresholds=thr)
+            assert ctx.last_batch_plan() is not None
+            for i, (Y, W) in enumerate(zip(Ys, want)):
+                _close(Y, W, "ragged member %d, cluster %d" % (i, cl))
+    finally:
+        ctx.set_tuning(0, 0, 0)
+
+
+def test_generic_and_strip_kernels_agree(gpu):
+    from lws_b200 import _native
+    p = gpu.lws(1024, 256)
+    A = np.abs(p.stft(make_signal("white", 9, 40000)))
+    thr = gpu.get_thresholds(20, 3.0, 0.15, 1)
+    a = gpu.batch_lws(A, p.W, thr)
+    b = gpu.batch_lws(A, p.W, thr, flags=_native.FORCE_GENERIC)
+    assert np.array_equal(a, b)
