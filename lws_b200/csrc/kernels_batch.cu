@@ -260,9 +260,204 @@ __device__ __forceinline__ void strip_update_block(RingCell<Q> &cell, const Stri
     }
 }
 
-// ---------------------------------------------------------------- the kernel
+// ---------------------------------------------------------------- software-pipelined block update (Q <= 4)
+// The reference fixes the ORDER in which the terms of a bin are added, not when their values
+// are computed: every inter-frame term  ar*(br+cr) - ai*(bi-ci)  depends only on neighbour frames,
+// so the values for bin i+1 are formed (loads included) while the additions, the square root and
+// the division of bin i -- one long dependent chain -- are in flight.  The code below is branch
+// free inside a block so that the instruction scheduler can interleave the two streams.
+//
+// PAT selects how the |W| > 1e-12 mask is applied: 1 = the pattern of the default sqrt-Hann
+// windows, known at compile time (r = 0: k = 1; r = Q/2: k in {0,1,2,4}; all other k set; the
+// host checks the actual mask against it), 0 = any mask, applied with selects at run time.
+template <int Q, int PAT>
+__device__ __forceinline__ constexpr bool pat_has(int r, int k)
+{
+    if (PAT == 0) return true;
+    if (r == 0) return k == 1;
+    if (2 * r == Q) return k == 0 || k == 1 || k == 2 || k == 4;
+    return true;
+}
+
+template <int FOLD>
+struct TermCount { static constexpr int per_r = FOLD == LWSB_FOLD_ANY ? 1 + 2 * SL : 1 + SL; };
+
 template <int Q, int FOLD>
-__global__ void __launch_bounds__(320, 1)
+struct BinTerms { // values of the inter-frame terms of one bin, in the reference's order of addition
+    static constexpr int N = (Q - 1) * TermCount<FOLD>::per_r;
+    double r[N], i[N];
+};
+
+__device__ __forceinline__ void pair_value(double ar, double ai, double br, double bi, double cr, double ci, double &vr, double &vi)
+{
+    vr = __dsub_rn(__dmul_rn(ar, __dadd_rn(br, cr)), __dmul_rn(ai, __dsub_rn(bi, ci)));
+    vi = __dadd_rn(__dmul_rn(ar, __dadd_rn(bi, ci)), __dmul_rn(ai, __dsub_rn(br, cr)));
+}
+
+// term values of frame pair (m - R_, m + R_) into slots [BASE, BASE + per_r)
+template <int Q, int P, int FOLD, int PAT, int R_, bool MINUS, int BASE>
+__device__ __forceinline__ void term_values_r(const RingCell<Q> &E, const StripW<Q> &w, BinTerms<Q, FOLD> &tv)
+{
+    constexpr int PN = (Q - P) % Q;
+    if (pat_has<Q, PAT>(R_, 0)) {
+        const double2 b = E(-R_, 0), c = E(+R_, 0);
+        pair_value(w.wr[P][R_][0], w.wi[P][R_][0], b.x, b.y, c.x, c.y, tv.r[BASE], tv.i[BASE]);
+    }
+#pragma unroll
+    for (int k = 1; k <= SL; ++k) {
+        if (FOLD == LWSB_FOLD_ANY) {
+            if (pat_has<Q, PAT>(R_, k)) {
+                const double2 b = E(-R_, -k), c = E(+R_, -k);
+                pair_value(w.wr[P][R_][k], w.wi[P][R_][k], b.x, b.y, c.x, c.y, tv.r[BASE + 2 * k - 1], tv.i[BASE + 2 * k - 1]);
+                const double2 b2 = E(+R_, +k), c2 = E(-R_, +k);
+                pair_value(w.wr[PN][R_][k], w.wi[PN][R_][k], b2.x, b2.y, c2.x, c2.y, tv.r[BASE + 2 * k], tv.i[BASE + 2 * k]);
+            }
+        } else if (pat_has<Q, PAT>(R_, k)) {
+            const double2 e1 = E(-R_, -k), e2 = E(+R_, +k), e3 = E(+R_, -k), e4 = E(-R_, +k);
+            double br, bi, cr, ci;
+            if (MINUS) {
+                br = __dsub_rn(e1.x, e2.x); bi = __dsub_rn(e1.y, e2.y);
+                cr = __dsub_rn(e3.x, e4.x); ci = __dsub_rn(e3.y, e4.y);
+            } else {
+                br = __dadd_rn(e1.x, e2.x); bi = __dadd_rn(e1.y, e2.y);
+                cr = __dadd_rn(e3.x, e4.x); ci = __dadd_rn(e3.y, e4.y);
+            }
+            pair_value(w.wr[P][R_][k], w.wi[P][R_][k], br, bi, cr, ci, tv.r[BASE + k], tv.i[BASE + k]);
+        }
+    }
+}
+
+// add the values of frame pair R_ in the reference's order
+template <int Q, int P, int FOLD, int PAT, int R_, int BASE>
+__device__ __forceinline__ void term_accumulate_r(const StripW<Q> &w, const BinTerms<Q, FOLD> &tv, double &tr, double &ti)
+{
+    constexpr int PN = (Q - P) % Q;
+    auto add = [&](int slot, unsigned flagword, int k) {
+        if (PAT == 1) { tr = __dadd_rn(tr, tv.r[slot]); ti = __dadd_rn(ti, tv.i[slot]); }
+        else {
+            const bool f = (flagword >> k) & 1u;
+            const double nr = __dadd_rn(tr, tv.r[slot]), ni = __dadd_rn(ti, tv.i[slot]);
+            tr = f ? nr : tr; ti = f ? ni : ti;
+        }
+    };
+    if (pat_has<Q, PAT>(R_, 0)) add(BASE, w.flag[P][R_], 0);
+#pragma unroll
+    for (int k = 1; k <= SL; ++k) {
+        if (!pat_has<Q, PAT>(R_, k)) continue;
+        if (FOLD == LWSB_FOLD_ANY) {
+            add(BASE + 2 * k - 1, w.flag[P][R_], k);
+            add(BASE + 2 * k, w.flag[PN][R_], k);
+        } else add(BASE + k, w.flag[P][R_], k);
+    }
+}
+
+template <int Q, int P, int FOLD, int PAT>
+__device__ __forceinline__ void bin_term_values(const RingCell<Q> &E, const StripW<Q> &w, BinTerms<Q, FOLD> &tv)
+{
+    constexpr int TPR = TermCount<FOLD>::per_r;
+    if constexpr (FOLD == LWSB_FOLD_Q4 && (P & 1)) { // odd bins: r = 1, 3 sign-flipped, then r = 2 (lwslib.cpp:186-235)
+        term_values_r<Q, P, FOLD, PAT, 1, true, 0>(E, w, tv);
+        term_values_r<Q, P, FOLD, PAT, 3, true, TPR>(E, w, tv);
+        term_values_r<Q, P, FOLD, PAT, 2, false, 2 * TPR>(E, w, tv);
+    } else {
+        if constexpr (Q > 1) term_values_r<Q, P, FOLD, PAT, 1, false, 0>(E, w, tv);
+        if constexpr (Q > 2) term_values_r<Q, P, FOLD, PAT, 2, false, TPR>(E, w, tv);
+        if constexpr (Q > 3) term_values_r<Q, P, FOLD, PAT, 3, false, 2 * TPR>(E, w, tv);
+    }
+}
+
+template <int Q, int P, int FOLD, int PAT>
+__device__ __forceinline__ void bin_accumulate(const StripW<Q> &w, const BinTerms<Q, FOLD> &tv, double &tr, double &ti)
+{
+    constexpr int TPR = TermCount<FOLD>::per_r;
+    if constexpr (FOLD == LWSB_FOLD_Q4 && (P & 1)) {
+        term_accumulate_r<Q, P, FOLD, PAT, 1, 0>(w, tv, tr, ti);
+        term_accumulate_r<Q, P, FOLD, PAT, 3, TPR>(w, tv, tr, ti);
+        term_accumulate_r<Q, P, FOLD, PAT, 2, 2 * TPR>(w, tv, tr, ti);
+    } else {
+        if constexpr (Q > 1) term_accumulate_r<Q, P, FOLD, PAT, 1, 0>(w, tv, tr, ti);
+        if constexpr (Q > 2) term_accumulate_r<Q, P, FOLD, PAT, 2, TPR>(w, tv, tr, ti);
+        if constexpr (Q > 3) term_accumulate_r<Q, P, FOLD, PAT, 3, 2 * TPR>(w, tv, tr, ti);
+    }
+}
+
+// bins I .. 7 of a block; `tv` holds the inter-frame term values of bin I on entry
+template <int Q, int FOLD, int PAT, int I>
+__device__ __forceinline__ void pipelined_block(RingCell<Q> &cell, const StripW<Q> &w, const BlockCtx &bc, const double *amp,
+                                                unsigned active, BinTerms<Q, FOLD> &tv, double2 *newv, unsigned &committed)
+{
+    if constexpr (I < SBK) {
+        constexpr int P = I % Q;
+        const int col = SL + SBK * bc.xb + I;
+        // (1) the next bin's inter-frame terms: independent of everything below
+        BinTerms<Q, FOLD> tvn;
+        if constexpr (I + 1 < SBK) {
+            cell.col = col + 1;
+            bin_term_values<Q, (I + 1) % Q, FOLD, PAT>(cell, w, tvn);
+        }
+        // (2) this bin: centre-frame terms (they see the bins just updated), then the ordered sum
+        cell.col = col;
+        double tr = 0.0, ti = 0.0;
+#pragma unroll
+        for (int k = 1; k <= SL; ++k)
+            if (pat_has<Q, PAT>(0, k)) {
+                const double2 b = cell(0, -k), c = cell(0, +k);
+                double vr, vi;
+                pair_value(w.wr[P][0][k], w.wi[P][0][k], b.x, b.y, c.x, c.y, vr, vi);
+                if (PAT == 1) { tr = __dadd_rn(tr, vr); ti = __dadd_rn(ti, vi); }
+                else {
+                    const bool f = (w.flag[P][0] >> k) & 1u;
+                    const double nr = __dadd_rn(tr, vr), ni = __dadd_rn(ti, vi);
+                    tr = f ? nr : tr; ti = f ? ni : ti;
+                }
+            }
+        bin_accumulate<Q, P, FOLD, PAT>(w, tv, tr, ti);
+        double2 val;
+        const bool ok = x_project(tr, ti, amp[I], val) && ((active >> I) & 1u);
+        // (3) commit: own cell and its mirrored copy (lwslib.cpp:356-368)
+        double2 *own = reinterpret_cast<double2 *>(bc.ring + bc.ownoff);
+        const int n = bc.n0 + I;
+        int mcol = col;
+        if (bc.first_strip && n >= 1 && n <= SL) mcol = SL - n;
+        else if (n >= bc.Nreal - 1 - SL && n <= bc.Nreal - 2) mcol = SL + 2 * (bc.Nreal - 1) - n - bc.b0;
+        if (ok) {
+            own[col] = val;
+            own[mcol] = make_double2(val.x, mcol == col ? val.y : -val.y);
+            committed |= 1u << I;
+        }
+        newv[I] = val;
+        if constexpr (I + 1 < SBK) pipelined_block<Q, FOLD, PAT, I + 1>(cell, w, bc, amp, active, tvn, newv, committed);
+    }
+}
+
+template <int Q, int FOLD, int PAT>
+__device__ __forceinline__ void strip_update_block_pipelined(RingCell<Q> &cell, const StripW<Q> &w, const BlockCtx &bc,
+                                                             const double *amp, unsigned active)
+{
+    BinTerms<Q, FOLD> tv;
+    cell.col = SL + SBK * bc.xb;
+    bin_term_values<Q, 0, FOLD, PAT>(cell, w, tv);
+    double2 newv[SBK];
+    unsigned committed = 0;
+    pipelined_block<Q, FOLD, PAT, 0>(cell, w, bc, amp, active, tv, newv, committed);
+    // halo copies in the neighbouring strips (distributed shared memory), edge blocks only
+    if (bc.xb == 0 && bc.ring_left) {
+        double2 *dst = reinterpret_cast<double2 *>(bc.ring_left + bc.ownoff) + SL + SBK * bc.NBr;
+#pragma unroll
+        for (int i = 0; i < SL; ++i)
+            if ((committed >> i) & 1u) dst[i] = newv[i];
+    }
+    if (bc.xb == bc.NBr - 1 && bc.ring_right) {
+        double2 *dst = reinterpret_cast<double2 *>(bc.ring_right + bc.ownoff);
+#pragma unroll
+        for (int i = SBK - SL; i < SBK; ++i)
+            if ((committed >> i) & 1u) dst[i - (SBK - SL)] = newv[i];
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int Q, int FOLD, int PAT>
+__global__ void __launch_bounds__(256, 1)
 k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ StripW<Q> w)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -448,7 +643,8 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                             bc.ring = ring; bc.ring_left = ring_left; bc.ring_right = ring_right;
                             bc.ownoff = cell.rowoff[Q - 1]; bc.xb = xb; bc.n0 = n0; bc.b0 = b0;
                             bc.Nreal = Nreal; bc.NBr = NBr; bc.first_strip = (c == 0);
-                            strip_update_block<Q, FOLD, 0>(cell, w, bc, amp, active);
+                            if constexpr (Q <= 4) strip_update_block_pipelined<Q, FOLD, PAT>(cell, w, bc, amp, active);
+                            else strip_update_block<Q, FOLD, 0>(cell, w, bc, amp, active);
                         }
                     }
                     cta_sync(); // macro-step t done
@@ -468,10 +664,10 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
 // ---------------------------------------------------------------- host side
 namespace {
 
-template <int Q, int FOLD>
+template <int Q, int FOLD, int PAT>
 cudaError_t launch_strips_t(const StripParams &prm, const StripW<Q> &w, const StripPlan &pl, int B, cudaStream_t s)
 {
-    auto kern = k_batch_strips<Q, FOLD>;
+    auto kern = k_batch_strips<Q, FOLD, PAT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
     if (e != cudaSuccess) return e;
     if (pl.C > 8) {
@@ -511,9 +707,25 @@ cudaError_t launch_strips_q(const StripParams &prm, const double *wr, const doub
             w.flag[p][r] = f;
         }
     w.fold = fold;
-    if (fold == LWSB_FOLD_ANY) return launch_strips_t<Q, LWSB_FOLD_ANY>(prm, w, pl, B, s);
-    if constexpr (Q == 4) { if (fold == LWSB_FOLD_Q4) return launch_strips_t<4, LWSB_FOLD_Q4>(prm, w, pl, B, s); }
-    if constexpr (Q == 2) { if (fold == LWSB_FOLD_Q2) return launch_strips_t<2, LWSB_FOLD_Q2>(prm, w, pl, B, s); }
+    // does the mask equal the default-window pattern the PAT = 1 kernels have compiled in?
+    bool def = Q <= 4;
+    for (int p = 0; p < Q && def; ++p)
+        for (int r = 0; r < Q && def; ++r)
+            for (int k = (r == 0 ? 1 : 0); k <= SL; ++k)
+                if (pat_has<Q, 1>(r, k) != (((w.flag[p][r] >> k) & 1u) != 0)) { def = false; break; }
+    if constexpr (Q <= 4) {
+        if (fold == LWSB_FOLD_ANY) return launch_strips_t<Q, LWSB_FOLD_ANY, 0>(prm, w, pl, B, s);
+        if constexpr (Q == 4) {
+            if (fold == LWSB_FOLD_Q4)
+                return def ? launch_strips_t<4, LWSB_FOLD_Q4, 1>(prm, w, pl, B, s) : launch_strips_t<4, LWSB_FOLD_Q4, 0>(prm, w, pl, B, s);
+        }
+        if constexpr (Q == 2) {
+            if (fold == LWSB_FOLD_Q2)
+                return def ? launch_strips_t<2, LWSB_FOLD_Q2, 1>(prm, w, pl, B, s) : launch_strips_t<2, LWSB_FOLD_Q2, 0>(prm, w, pl, B, s);
+        }
+    } else {
+        if (fold == LWSB_FOLD_ANY) return launch_strips_t<Q, LWSB_FOLD_ANY, 0>(prm, w, pl, B, s);
+    }
     return cudaErrorInvalidValue;
 }
 
@@ -543,7 +755,7 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
         if (smem_limit < fixed + rowbytes * 8) continue;
         const int Rmax = (int)((smem_limit - fixed) / (rowbytes + 8));
         int G = (Rmax - (Q - 1) - SLEAD - NS - 1) / Q;
-        G = std::min(G, (320 - 32) / NS);
+        G = std::min(G, (256 - 32) / NS);
         G = std::min(G, iters);
         if (max_sweeps > 0) G = std::min(G, max_sweeps);
         if (G < 1) continue;
