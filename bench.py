@@ -341,6 +341,7 @@ def run_b200_arm(args):
                          "note": "fp64 stencil: the kernel is bounded by the fp64 pipe, not HBM (DESIGN.md)"},
             "cpu_baseline": cpu,
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
+            "plan": ctx.last_batch_plan(), "cycles_cluster0": ctx.last_batch_cycles(),
             "kernel_share_of_step": k_ms * args.steps / dev_ms if dev_ms else None,
         }
         print(json.dumps(line), flush=True)

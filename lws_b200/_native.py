@@ -53,6 +53,7 @@ SIGNATURES = {
     "lwsb_debug_terms": (_ci, [_dp, _dp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ip, _ip, _dp, _dp]),
     "lwsb_debug_plan_strips": (_ci, [_ci, _ci, _ci, _ci, _ci, _ci, _ll, _ci, _ci, _ci, _ip]),
     "lwsb_set_tuning": (_ci, [_vp, _ll, _ci, _ci]),
+    "lwsb_last_batch_cycles": (_ci, [_vp, ctypes.POINTER(ctypes.c_ulonglong)]),
     "lwsb_debug_online_chain_length": (_ll, [_ci, _ci, _ci]),
     "lwsb_debug_online_task": (_ci, [_ci, _ci, _ci, _ci, _ll, _ip, _ip, _ip, _ip, _ip]),
 }
@@ -257,14 +258,19 @@ class Context(object):
     def set_tuning(self, smem_limit=0, cluster=0, sweeps_per_pass=0):
         self._c(lib().lwsb_set_tuning(self._h, int(smem_limit), int(cluster), int(sweeps_per_pass)))
 
+    def last_batch_cycles(self):
+        out = (ctypes.c_ulonglong * 7)()
+        if self._c(lib().lwsb_last_batch_cycles(self._h, out)) != 1:
+            return None
+        keys = ("ctrl_publish", "ctrl_poll", "ctrl_tma", "warp_work", "warp_wait_strip", "warp_wait_neighbours", "warps")
+        return dict(zip(keys, [int(x) for x in out]))
+
     def last_batch_plan(self):
         """dict describing the cluster strip plan of the last batch() call, or None (generic kernel)."""
-        out = (ctypes.c_int * 9)()
+        out = (ctypes.c_int * 10)()
         if self._c(lib().lwsb_last_batch_plan(self._h, out)) != 1:
             return None
-        keys = ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots", "sweeps_per_pass", "ring_rows",
-                "ring_pitch", "threads", "smem_bytes")
-        return dict(zip(keys, list(out)))
+        return dict(zip(PLAN_KEYS, list(out)))
 
     def launch_count(self):
         return int(lib().lwsb_launch_count(self._h))
@@ -296,11 +302,11 @@ def debug_terms(Wc, fold, rframe, cframe, p):
 
 
 PLAN_KEYS = ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots", "sweeps_per_pass", "ring_rows",
-             "ring_pitch", "threads", "smem_bytes")
+             "ring_pitch", "threads", "smem_bytes", "sweep_lag")
 
 
 def debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit=232448, sm_count=148, cluster=0, sweeps=0):
-    out = (ctypes.c_int * 9)()
+    out = (ctypes.c_int * 10)()
     if _check(lib().lwsb_debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit, sm_count, cluster, sweeps,
                                            out)) != 1:
         return None

@@ -392,8 +392,8 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
                                     c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps) &&
                         c->P >= strips_min_pitch(c->Nreal, c->c0);
     if (strips) {
-        CU(c, c->status.reserve(sizeof(unsigned)));
-        CU(c, cudaMemsetAsync(c->status.p, 0, sizeof(unsigned), c->stream));
+        CU(c, c->status.reserve(128));
+        CU(c, cudaMemsetAsync(c->status.p, 0, 128, c->stream));
         if (int r = begin_compute(c)) return r;
         CU(c, launch_batch_strips(c->view(), c->w[LWSB_W].wr.data(), c->w[LWSB_W].wi.data(), fold,
                                   c->dthr.as<const double>(), c->max_amp.as<const double>(), iterations, pl,
@@ -666,6 +666,17 @@ extern "C" int lwsb_last_compute_ms(lwsb_ctx *c, float *ms)
 
 extern "C" long long lwsb_launch_count(const lwsb_ctx *c) { return c ? c->launches : 0; }
 
+extern "C" int lwsb_last_batch_cycles(lwsb_ctx *c, unsigned long long *out7)
+{
+    CHECK_CTX(c);
+    if (!out7) return fail(c, LWSB_ERR_ARG, "out7 is NULL");
+    if (c->last_kernel != 1 || !c->status.p) return 0;
+    if (int r = use_device(c)) return r;
+    CU(c, cudaMemcpyAsync(out7, c->status.as<char>() + 8, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 1;
+}
+
 extern "C" int lwsb_set_tuning(lwsb_ctx *c, long long smem_limit, int cluster, int sweeps_per_pass)
 {
     CHECK_CTX(c);
@@ -680,8 +691,8 @@ extern "C" int lwsb_last_batch_plan(const lwsb_ctx *c, int *out9)
     if (!c || !out9) return LWSB_ERR_ARG;
     if (c->last_kernel != 1) return 0;
     const StripPlan &p = c->last_plan;
-    const int v[9] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes};
-    for (int i = 0; i < 9; ++i) out9[i] = v[i];
+    const int v[10] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS};
+    for (int i = 0; i < 10; ++i) out9[i] = v[i];
     return 1;
 }
 
@@ -734,8 +745,8 @@ extern "C" int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, i
     if (!out9) return LWSB_ERR_ARG;
     StripPlan p;
     if (!plan_strips(Nreal, Q, L, iterations, maxT, B, (size_t)smem_limit, sm_count, &p, force_cluster, max_sweeps)) return 0;
-    const int v[9] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes};
-    for (int i = 0; i < 9; ++i) out9[i] = v[i];
+    const int v[10] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS};
+    for (int i = 0; i < 10; ++i) out9[i] = v[i];
     return 1;
 }
 

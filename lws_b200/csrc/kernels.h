@@ -29,7 +29,7 @@ void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, in
 
 // kernels_batch.cu
 struct StripPlan {
-    int C, NBr, NBV, NS, G, R, pitch, nthreads, smem_bytes;
+    int C, NBr, NBV, NS, G, R, pitch, nthreads, smem_bytes, QS;
 };
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
                  int force_cluster = 0, int max_sweeps = 0);

@@ -57,7 +57,7 @@ struct StripParams {
     const double *thr;         // [iters] unscaled thresholds
     const double *max_amp;     // [B]
     int iters;
-    int C, NBr, NBV, NS, G, R, pitch;
+    int C, NBr, NBV, NS, G, R, pitch, QS;
     unsigned *status;          // [0]: 0 ok, else first watchdog code
 };
 
@@ -470,6 +470,7 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
     const int lane = tid & 31;
     const LwsbView &v = prm.v;
     const int NBr = prm.NBr, NBV = prm.NBV, NS = prm.NS, G = prm.G, R = prm.R, pitch = prm.pitch;
+    const int QS = prm.QS; // frames between consecutive sweeps (>= Q; odd so that a warp's rows spread over all banks)
     const int Nreal = v.Nreal, P = v.P;
     const unsigned rowbytes = (unsigned)pitch * 16u;
 
@@ -494,10 +495,11 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
     const int wb_hi = c == C - 1 ? SL + (Nreal - b0) + SL : SL + SBK * NBr;
 
     // per-thread slot: frame residue j, sweep slot g
-    const int j = tid % NS, g = tid / NS;
-    const bool has_slot = !is_ctrl && g < G;
+    const int j = tid / G, g = tid % G; // sweep slot fastest: the lanes of a quarter-warp sit QS rows apart
+    const bool has_slot = !is_ctrl && j < NS;
 
     bool mbar_live = false;
+    long long tm_publish = 0, tm_poll = 0, tm_house = 0, tm_work = 0, tm_waitA = 0, tm_waitB = 0; // cycle counters (status[2..])
     for (int u = cid; u < v.B; u += ncl) {
         const int T = v.T[u];
         const int Tp = T + 2 * (Q - 1);
@@ -516,7 +518,7 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
         const int npass = (n_act + G - 1) / G;
         for (int pass = 0; pass < npass; ++pass) {
             const int Gp = min(G, n_act - pass * G);
-            const int nsteps = 2 * (T - 1 + Q * (Gp - 1)) + NBV;
+            const int nsteps = 2 * (T - 1 + QS * (Gp - 1)) + NBV;
             const double thr = (has_slot && g < Gp) ? __dmul_rn(prm.thr[act[pass * G + g]], mean) : 0.0; // lws.pyx:245
 
             // ---- pass prologue: previous pass fully written back everywhere, ring (re)initialised
@@ -559,6 +561,7 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                 cta_sync(); // releases the compute warps into macro-step 0
                 for (int t = 0; t < nsteps; ++t) {
                     cta_sync(); // macro-step t computed by every thread of the strip
+                    const long long c0 = clock64();
                     if (lane == 0) {
                         // publish first: the neighbours' next macro-step waits for this one.  (Polling for
                         // step t+1 before publishing step t would dead-lock: in lock step the neighbour's
@@ -566,10 +569,18 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                         const unsigned done = (unsigned)(t + 1);
                         if (flag_at_left) st_release_cluster(flag_at_left, done);
                         if (flag_at_right) st_release_cluster(flag_at_right, done);
+                    }
+                    const long long c1 = clock64();
+                    if (t + 1 < nsteps) poll(t + 1);
+                    __syncwarp();
+                    const long long c2 = clock64();
+                    cta_sync(); // releases the compute warps into macro-step t + 1
+                    // TMA traffic, overlapped with macro-step t + 1: nothing below touches a row in use
+                    if (lane == 0) {
                         // frame whose last sweep of this pass finished its last real block in step t
                         const int tf = t - (nb_my - 1);
                         if (nb_my > 0 && tf >= 0 && (tf & 1) == 0) {
-                            const int m = tf / 2 - Q * (Gp - 1);
+                            const int m = tf / 2 - QS * (Gp - 1);
                             if (m >= 0 && m < T) {
                                 const int e = m + Q - 1;
                                 fence_proxy_async();
@@ -588,9 +599,8 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                             }
                         }
                     }
-                    if (t + 1 < nsteps) poll(t + 1);
                     __syncwarp();
-                    cta_sync(); // releases the compute warps into macro-step t + 1
+                    tm_publish += c1 - c0; tm_poll += c2 - c1; tm_house += clock64() - c2;
                 }
                 // Slot s received Tp/R (+1) rows in this pass, one mbarrier phase each.  The waits address
                 // phases by parity counted from the start of the pass, so slots that saw an odd number of
@@ -601,9 +611,10 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
             } else {
                 // ================= compute warps =================
                 int xb = -2 * j;          // block index; negative while the slot has not started
-                int m = j - Q * g;        // frame of the slot
+                int m = j - QS * g;       // frame of the slot
                 cta_sync();               // control warp has verified macro-step 0
                 for (int t = 0; t < nsteps; ++t) {
+                    const long long k0 = clock64();
                     if ((t & 1) == 0) {
                         // rows entering use at this frame clock must have landed
                         const int k = t >> 1;
@@ -647,14 +658,28 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                             else strip_update_block<Q, FOLD, 0>(cell, w, bc, amp, active);
                         }
                     }
+                    const long long k1 = clock64();
                     cta_sync(); // macro-step t done
                     if (++xb == NBV) { xb = 0; m += NS; }
+                    const long long k2 = clock64();
                     cta_sync(); // neighbours ready for macro-step t + 1
+                    tm_work += k1 - k0; tm_waitA += k2 - k1; tm_waitB += clock64() - k2;
                 }
             }
         }
         // ---- utterance epilogue: everything written back before the ring is reused
         if (is_ctrl && lane == 0) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
+    }
+    // cycle accounting of cluster 0 (introspection: lwsb_last_batch_cycles): control lane and one lane per compute warp
+    if (cid == 0 && lane == 0) {
+        unsigned long long *acc = reinterpret_cast<unsigned long long *>(prm.status + 2);
+        if (is_ctrl) {
+            atomicAdd(acc + 0, (unsigned long long)tm_publish); atomicAdd(acc + 1, (unsigned long long)tm_poll);
+            atomicAdd(acc + 2, (unsigned long long)tm_house);
+        } else {
+            atomicAdd(acc + 3, (unsigned long long)tm_work); atomicAdd(acc + 4, (unsigned long long)tm_waitA);
+            atomicAdd(acc + 5, (unsigned long long)tm_waitB); atomicAdd(acc + 6, 1ull);
+        }
     }
     cluster.sync(); // no CTA leaves while a neighbour may still address its shared memory
 }
@@ -754,23 +779,40 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
         const size_t fixed = 64 + 16 + (size_t)(iters + 8) * sizeof(int) + 256;
         if (smem_limit < fixed + rowbytes * 8) continue;
         const int Rmax = (int)((smem_limit - fixed) / (rowbytes + 8));
-        int G = (Rmax - (Q - 1) - SLEAD - NS - 1) / Q;
-        G = std::min(G, (256 - 32) / NS);
-        G = std::min(G, iters);
-        if (max_sweeps > 0) G = std::min(G, max_sweeps);
-        if (G < 1) continue;
-        const int npass = (iters + G - 1) / G;
-        G = (iters + npass - 1) / npass; // same number of passes, evenly filled
-        const int R = Q * G + Q + SLEAD + NS;
         const int ncl = std::max(1, (sm_count * 9 / 10) / C); // GPC packing loses a few SMs to clusters
         const double rounds = std::ceil((double)B / ncl);
-        const double steps = 2.0 * (maxT + Q * G) + NBV + (C - 1) * NBr;
-        const double cost = rounds * npass * steps * (std::max(NS * G, 64) + 24.0);
-        if (!found || cost < best) {
-            found = true; best = cost;
-            out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->R = R; out->pitch = pitch;
-            out->nthreads = (NS * G + 31) / 32 * 32 + 32;
-            out->smem_bytes = (int)(fixed + (size_t)R * (rowbytes + 8));
+        // sweep lag: Q frames is the minimum; an odd lag lets the sweep-fastest thread order be bank-conflict free
+        for (int QS = Q; QS <= Q + 1; ++QS) {
+            if (Rmax < 2 * Q + SLEAD + NS) continue;
+            int Gmax = (Rmax - 2 * Q - SLEAD - NS) / QS + 1;
+            Gmax = std::min(Gmax, (256 - 32) / NS);
+            Gmax = std::min(Gmax, iters);
+            if (max_sweeps > 0) Gmax = std::min(Gmax, max_sweeps);
+            for (int G = Gmax; G >= 1 && G > Gmax - 8; --G) {
+                // shared-memory wavefronts per 128-bit warp access: the 8 lanes of a quarter-warp hit
+                // 16-byte bank groups (j - QS*g) mod 8 (odd pitch); the busiest group sets the count
+                double waves = 0.0; int quarters = 0;
+                for (int q0 = 0; q0 < NS * G; q0 += 8) {
+                    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+                    for (int tid = q0; tid < q0 + 8 && tid < NS * G; ++tid) {
+                        const int b = (((tid / G) - QS * (tid % G)) % 8 + 8) % 8;
+                        mx = std::max(mx, ++cnt[b]);
+                    }
+                    waves += mx; ++quarters;
+                }
+                const double f = waves / quarters;
+                const int npass = (iters + G - 1) / G;
+                const double steps = 2.0 * (maxT + QS * G) + NBV + (C - 1) * NBr;
+                const double warps = NS * G / 32.0;
+                const double cost = rounds * npass * (steps * (1888.0 * f * warps + (C > 1 ? 3000.0 : 1000.0)) + 40000.0);
+                if (!found || cost < best) {
+                    found = true; best = cost;
+                    out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS;
+                    out->R = QS * (G - 1) + 2 * Q + SLEAD + NS;
+                    out->nthreads = (NS * G + 31) / 32 * 32 + 32;
+                    out->smem_bytes = (int)(fixed + (size_t)out->R * (rowbytes + 8));
+                }
+            }
         }
     }
     return found;
@@ -788,7 +830,7 @@ cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const 
 {
     StripParams prm;
     prm.v = v; prm.thr = thr; prm.max_amp = max_amp; prm.iters = iters;
-    prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch;
+    prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch; prm.QS = pl.QS;
     prm.status = status;
     switch (v.Q) {
     case 2: return launch_strips_q<2>(prm, wr_host, wi_host, fold, pl, v.B, s);

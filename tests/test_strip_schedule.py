@@ -40,14 +40,16 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
     """One call of `len(thr_list)` sweeps on the extended spectrogram E (modified in place)."""
     C, NBr, NBV, NS, G, R = (plan[k] for k in ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots",
                                                 "sweeps_per_pass", "ring_rows"))
+    QS = plan["sweep_lag"]
+    assert QS >= Q
     Tp = T + 2 * (Q - 1)
     amax = A[Q - 1:Q - 1 + T, SL:SL + Nreal].max()
     act = [i for i, th in enumerate(thr_list) if th * mean < amax]
     npass = (len(act) + G - 1) // G
-    assert R >= Q * G + Q + SLEAD + NS
+    assert R >= QS * (G - 1) + 2 * Q + SLEAD + NS
     for ps in range(npass):
         Gp = min(G, len(act) - ps * G)
-        nsteps = 2 * (T - 1 + Q * (Gp - 1)) + NBV
+        nsteps = 2 * (T - 1 + QS * (Gp - 1)) + NBV
         strips = [Strip(c, plan, Nreal) for c in range(C)]
 
         def load(st, e):
@@ -73,7 +75,7 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
                         d = t - 2 * j
                         if d < 0:
                             continue
-                        xb, m = d % NBV, j + NS * (d // NBV) - Q * g
+                        xb, m = d % NBV, j + NS * (d // NBV) - QS * g
                         if not (xb < st.nb_my and 0 <= m < T):
                             continue
                         me = (st.c, g, j)
@@ -127,7 +129,7 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
                     continue
                 tf = t - (st.nb_my - 1)
                 if st.nb_my > 0 and tf >= 0 and tf % 2 == 0:
-                    m = tf // 2 - Q * (Gp - 1)
+                    m = tf // 2 - QS * (Gp - 1)
                     if 0 <= m < T:
                         e = m + Q - 1
                         assert st.tag[e % R] == e
@@ -207,7 +209,7 @@ def test_planner_properties():
                         assert NBV % 2 == 0 and NBV >= NBr and NS * 2 == NBV and NBr >= 2
                         assert C * NBr * SBK >= Nreal                          # the strips cover every bin
                         assert (C - 1) * NBr * SBK <= Nreal - 1 - SL           # mirror zone inside the last strip
-                        assert R >= Q * G + Q + SLEAD + NS and 1 <= G <= iters
+                        assert R >= pl["sweep_lag"] * (G - 1) + 2 * Q + SLEAD + NS and 1 <= G <= iters and pl["sweep_lag"] >= Q
                         assert pl["ring_pitch"] % 2 == 1 and pl["ring_pitch"] >= SBK * NBr + 2 * SL
                         assert pl["smem_bytes"] <= smem and pl["threads"] <= 256 and pl["threads"] >= NS * G + 32
                         assert R * pl["ring_pitch"] * 16 + R * 8 + 32 + 4 * iters <= pl["smem_bytes"]
