@@ -128,7 +128,7 @@ int lwsb_istft(lwsb_ctx *ctx, const void *S_in, int B, int M, int Nreal, const d
 int lwsb_last_compute_ms(lwsb_ctx *ctx, float *ms);
 long long lwsb_launch_count(const lwsb_ctx *ctx); /* kernels launched by this context so far */
 /* 1 and the plan {cluster size, blocks per strip, virtual blocks, frame slots, sweeps per pass, ring rows,
- * ring pitch, threads, shared-memory bytes, frames between sweeps} (10 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it
+ * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order} (11 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it
  * ran the generic wavefront kernel */
 int lwsb_last_batch_plan(const lwsb_ctx *ctx, int *out9);
 /* tuning knobs of the strip kernel's planner (0 = automatic): shared-memory budget per CTA in bytes, cluster
@@ -150,7 +150,7 @@ int lwsb_get_stats(lwsb_ctx *ctx, double *mean_amp, double *max_amp);
  *    into (row, weight set, rframe, cframe, threshold index or -1). */
 int lwsb_debug_terms(const double *wr, const double *wi, int Q, int L, int fold, int rframe, int cframe, int p,
                      int max_terms, int *dr, int *dk, double *cr, double *ci);
-/*  - lwsb_debug_plan_strips: the plan the cluster strip kernel would use (same 10 numbers as
+/*  - lwsb_debug_plan_strips: the plan the cluster strip kernel would use (same 11 numbers as
  *    lwsb_last_batch_plan) for a shape and a shared-memory / SM budget; returns 0 when the generic kernel serves it. */
 int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, int maxT, int B, long long smem_limit,
                            int sm_count, int force_cluster, int max_sweeps, int *out9);

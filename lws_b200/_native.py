@@ -267,7 +267,7 @@ class Context(object):
 
     def last_batch_plan(self):
         """dict describing the cluster strip plan of the last batch() call, or None (generic kernel)."""
-        out = (ctypes.c_int * 10)()
+        out = (ctypes.c_int * 11)()
         if self._c(lib().lwsb_last_batch_plan(self._h, out)) != 1:
             return None
         return dict(zip(PLAN_KEYS, list(out)))
@@ -302,11 +302,11 @@ def debug_terms(Wc, fold, rframe, cframe, p):
 
 
 PLAN_KEYS = ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots", "sweeps_per_pass", "ring_rows",
-             "ring_pitch", "threads", "smem_bytes", "sweep_lag")
+             "ring_pitch", "threads", "smem_bytes", "sweep_lag", "sweep_fastest")
 
 
 def debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit=232448, sm_count=148, cluster=0, sweeps=0):
-    out = (ctypes.c_int * 10)()
+    out = (ctypes.c_int * 11)()
     if _check(lib().lwsb_debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit, sm_count, cluster, sweeps,
                                            out)) != 1:
         return None

@@ -64,6 +64,7 @@ struct lwsb_ctx {
     int last_kernel = 0;                   // 0 generic, 1 strips (introspection)
     long long tune_smem = 0;               // tuning knobs (lwsb_set_tuning): shared-memory budget, cluster size,
     int tune_cluster = 0, tune_sweeps = 0; // sweeps per pass; 0 = automatic
+    int tune_lag = 0;                      // frames between sweeps (env LWSB_STRIP_LAG only)
     StripPlan last_plan{};
     std::map<int, DevBuf> twiddles;        // exp(-2 pi i j / N) tables by N
     std::vector<void *> hptr;
@@ -180,6 +181,7 @@ extern "C" int lwsb_create(int device, void *stream, lwsb_ctx **out)
     if (const char *e1 = getenv("LWSB_STRIP_SMEM")) c->tune_smem = atoll(e1);
     if (const char *e2 = getenv("LWSB_STRIP_CLUSTER")) c->tune_cluster = atoi(e2);
     if (const char *e3 = getenv("LWSB_STRIP_SWEEPS")) c->tune_sweeps = atoi(e3);
+    if (const char *e4 = getenv("LWSB_STRIP_LAG")) c->tune_lag = atoi(e4);
     *out = c;
     return LWSB_OK;
 }
@@ -389,7 +391,7 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
                         plan_strips(c->Nreal, c->Q, c->L, iterations, c->maxT, c->B,
                                     c->tune_smem > 0 ? std::min((size_t)c->tune_smem, c->prop.sharedMemPerBlockOptin)
                                                      : c->prop.sharedMemPerBlockOptin,
-                                    c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps) &&
+                                    c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps, c->tune_lag) &&
                         c->P >= strips_min_pitch(c->Nreal, c->c0);
     if (strips) {
         CU(c, c->status.reserve(128));
@@ -691,8 +693,8 @@ extern "C" int lwsb_last_batch_plan(const lwsb_ctx *c, int *out9)
     if (!c || !out9) return LWSB_ERR_ARG;
     if (c->last_kernel != 1) return 0;
     const StripPlan &p = c->last_plan;
-    const int v[10] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS};
-    for (int i = 0; i < 10; ++i) out9[i] = v[i];
+    const int v[11] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST};
+    for (int i = 0; i < 11; ++i) out9[i] = v[i];
     return 1;
 }
 
@@ -744,9 +746,9 @@ extern "C" int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, i
 {
     if (!out9) return LWSB_ERR_ARG;
     StripPlan p;
-    if (!plan_strips(Nreal, Q, L, iterations, maxT, B, (size_t)smem_limit, sm_count, &p, force_cluster, max_sweeps)) return 0;
-    const int v[10] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS};
-    for (int i = 0; i < 10; ++i) out9[i] = v[i];
+    if (!plan_strips(Nreal, Q, L, iterations, maxT, B, (size_t)smem_limit, sm_count, &p, force_cluster, max_sweeps, 0)) return 0;
+    const int v[11] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST};
+    for (int i = 0; i < 11; ++i) out9[i] = v[i];
     return 1;
 }
 

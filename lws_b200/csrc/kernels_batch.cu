@@ -57,7 +57,7 @@ struct StripParams {
     const double *thr;         // [iters] unscaled thresholds
     const double *max_amp;     // [B]
     int iters;
-    int C, NBr, NBV, NS, G, R, pitch, QS;
+    int C, NBr, NBV, NS, G, R, pitch, QS, GFAST;
     unsigned *status;          // [0]: 0 ok, else first watchdog code
 };
 
@@ -495,8 +495,10 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
     const int wb_hi = c == C - 1 ? SL + (Nreal - b0) + SL : SL + SBK * NBr;
 
     // per-thread slot: frame residue j, sweep slot g
-    const int j = tid / G, g = tid % G; // sweep slot fastest: the lanes of a quarter-warp sit QS rows apart
-    const bool has_slot = !is_ctrl && j < NS;
+    // thread order: sweep slot fastest (lanes of a quarter-warp sit QS rows apart: conflict free for odd QS) or
+    // frame slot fastest (lanes on consecutive frames); the planner picks the one with fewer bank conflicts
+    const int j = prm.GFAST ? tid / G : tid % NS, g = prm.GFAST ? tid % G : tid / NS;
+    const bool has_slot = !is_ctrl && j < NS && g < G;
 
     bool mbar_live = false;
     long long tm_publish = 0, tm_poll = 0, tm_house = 0, tm_work = 0, tm_waitA = 0, tm_waitB = 0; // cycle counters (status[2..])
@@ -547,14 +549,18 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                     if (c > 0) {
                         const unsigned need = (unsigned)min(t + NBr, nsteps);
                         unsigned spins = 0;
-                        while (ld_acquire_cluster(&flags[0]) < need)
+                        while (ld_acquire_cluster(&flags[0]) < need) {
+                            __nanosleep(32); // the control warp shares an issue port with a compute warp
                             if (!keep_waiting(spins, prm.status, 0x10000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
+                        }
                     }
                     if (c < C - 1 && t - NBr > 0) {
                         const unsigned need = (unsigned)(t - NBr);
                         unsigned spins = 0;
-                        while (ld_acquire_cluster(&flags[1]) < need)
+                        while (ld_acquire_cluster(&flags[1]) < need) {
+                            __nanosleep(32);
                             if (!keep_waiting(spins, prm.status, 0x20000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
+                        }
                     }
                 };
                 poll(0);
@@ -759,7 +765,7 @@ cudaError_t launch_strips_q(const StripParams &prm, const double *wr, const doub
 // Chooses cluster size, strip width and sweeps per pass.  Returns false when the shape is not
 // served by this kernel (the generic kernel takes over).
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
-                 int force_cluster, int max_sweeps)
+                 int force_cluster, int max_sweeps, int force_lag)
 {
     if (L != SL || !(Q == 2 || Q == 4 || Q == 8) || iters < 1) return false;
     const int nbt = (Nreal + SBK - 1) / SBK; // blocks holding real bins
@@ -791,23 +797,27 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
             for (int G = Gmax; G >= 1 && G > Gmax - 8; --G) {
                 // shared-memory wavefronts per 128-bit warp access: the 8 lanes of a quarter-warp hit
                 // 16-byte bank groups (j - QS*g) mod 8 (odd pitch); the busiest group sets the count
-                double waves = 0.0; int quarters = 0;
-                for (int q0 = 0; q0 < NS * G; q0 += 8) {
-                    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
-                    for (int tid = q0; tid < q0 + 8 && tid < NS * G; ++tid) {
-                        const int b = (((tid / G) - QS * (tid % G)) % 8 + 8) % 8;
-                        mx = std::max(mx, ++cnt[b]);
+                double f = 0.0; int gfast = 0;
+                for (int order = 0; order < 2; ++order) {
+                    double waves = 0.0; int quarters = 0;
+                    for (int q0 = 0; q0 < NS * G; q0 += 8) {
+                        int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+                        for (int tid = q0; tid < q0 + 8 && tid < NS * G; ++tid) {
+                            const int jj = order ? tid / G : tid % NS, gg = order ? tid % G : tid / NS;
+                            mx = std::max(mx, ++cnt[((jj - QS * gg) % 8 + 8) % 8]);
+                        }
+                        waves += mx; ++quarters;
                     }
-                    waves += mx; ++quarters;
+                    if (order == 0 || waves / quarters < f) { f = waves / quarters; gfast = order; }
                 }
-                const double f = waves / quarters;
+                if (force_lag > 0 && QS != force_lag) continue;
                 const int npass = (iters + G - 1) / G;
                 const double steps = 2.0 * (maxT + QS * G) + NBV + (C - 1) * NBr;
                 const double warps = NS * G / 32.0;
-                const double cost = rounds * npass * (steps * (1888.0 * f * warps + (C > 1 ? 3000.0 : 1000.0)) + 40000.0);
+                const double cost = rounds * npass * (steps * (15000.0 + 900.0 * f * warps + (C > 1 ? 2500.0 * (C > 2 ? 1.0 : 0.5) : 0.0)) + 60000.0);
                 if (!found || cost < best) {
                     found = true; best = cost;
-                    out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS;
+                    out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast;
                     out->R = QS * (G - 1) + 2 * Q + SLEAD + NS;
                     out->nthreads = (NS * G + 31) / 32 * 32 + 32;
                     out->smem_bytes = (int)(fixed + (size_t)out->R * (rowbytes + 8));
@@ -830,7 +840,7 @@ cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const 
 {
     StripParams prm;
     prm.v = v; prm.thr = thr; prm.max_amp = max_amp; prm.iters = iters;
-    prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch; prm.QS = pl.QS;
+    prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch; prm.QS = pl.QS; prm.GFAST = pl.GFAST;
     prm.status = status;
     switch (v.Q) {
     case 2: return launch_strips_q<2>(prm, wr_host, wi_host, fold, pl, v.B, s);
