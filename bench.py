@@ -208,21 +208,68 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(sm)}
 
 
+class Ranks(object):
+    """One process per GPU (torchrun): utterances are independent, so the only traffic between
+    ranks is the barrier around the timed region and a MAX over the per-rank device times."""
+
+    def __init__(self, backend):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.backend = backend
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            if backend == "nccl":
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            else:
+                dist.init_process_group(backend)
+
+    def barrier(self):
+        if self.backend == "nccl":
+            self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        if self.backend == "nccl":
+            self.torch.cuda.synchronize()
+
+    def max(self, x):
+        dev = "cuda" if self.backend == "nccl" else "cpu"
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x):
+        dev = "cuda" if self.backend == "nccl" else "cpu"
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def throughput(units_per_rank_step, steps, world_units_factor, seconds_max):
+    """whole-job units per second: every rank did `units_per_rank_step` per step; time = max over ranks"""
+    return units_per_rank_step * world_units_factor * steps / seconds_max
+
+
 def run_b200_arm(args):
     import torch
-    import torch.distributed as dist
     import lws_b200
     from lws_b200 import _native
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU path)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    ranks = Ranks("nccl")
+    world, rank, local = ranks.world, ranks.rank, ranks.local
     name = args.workload
     idx, B, n, fs, hop, it = WORKLOADS[name]
     thr = thresholds_for(name, args.thresholds)
@@ -250,11 +297,7 @@ def run_b200_arm(args):
         ctx.batch(thr)
         ctx.store_device(out_ptrs)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = ranks.barrier
 
     for _ in range(args.warmup):
         step_device()
@@ -279,11 +322,9 @@ def run_b200_arm(args):
     dev_ms = ev[0].elapsed_time(ev[1])
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(t.item())
-    value = bins_rank * world * args.steps / (dev_ms_max * 1e-3)
+    dev_ms_max = ranks.max(dev_ms)
+    bins_all = ranks.sum(bins_rank)  # every rank holds its own utterances (weak scaling)
+    value = throughput(bins_all / world, args.steps, world, dev_ms_max * 1e-3)
 
     # ---- e2e: public API, pinned host in/out, H2D + D2H inside the timed region
     A_pin = torch.from_numpy(A_host).pin_memory()
@@ -299,10 +340,7 @@ def run_b200_arm(args):
         chk = float(np.abs(Y_np[0, 0, 0]))  # the step's result is read on the host
     barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = bins_rank * world * args.steps / float(t.item())
+    e2e_value = throughput(bins_all / world, args.steps, world, ranks.max(e2e_s))
 
     # sanity: device-resident and host paths agree bit for bit, magnitudes preserved
     Yd = Y_dev.cpu().numpy()
@@ -346,8 +384,7 @@ def run_b200_arm(args):
         }
         print(json.dumps(line), flush=True)
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    ranks.close()
     return 0
 
 
