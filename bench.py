@@ -223,6 +223,7 @@ class Ranks(object):
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29500")
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
             if backend == "nccl":
                 dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             else:
