@@ -128,16 +128,19 @@ int lwsb_istft(lwsb_ctx *ctx, const void *S_in, int B, int M, int Nreal, const d
 int lwsb_last_compute_ms(lwsb_ctx *ctx, float *ms);
 long long lwsb_launch_count(const lwsb_ctx *ctx); /* kernels launched by this context so far */
 /* 1 and the plan {cluster size, blocks per strip, virtual blocks, frame slots, sweeps per pass, ring rows,
- * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order} (11 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it
+ * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order, tensor-memory variant} (12 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it
  * ran the generic wavefront kernel */
 int lwsb_last_batch_plan(const lwsb_ctx *ctx, int *out9);
 /* tuning knobs of the strip kernel's planner (0 = automatic): shared-memory budget per CTA in bytes, cluster
  * size (1, 2, 4, 8) and sweeps in flight per pass.  Also settable through the environment variables
- * LWSB_STRIP_SMEM / LWSB_STRIP_CLUSTER / LWSB_STRIP_SWEEPS read by lwsb_create().  Results do not depend on them. */
+ * LWSB_STRIP_SMEM / LWSB_STRIP_CLUSTER / LWSB_STRIP_SWEEPS (and LWSB_STRIP_LAG, LWSB_STRIP_TM) read by lwsb_create().  Results do not depend on them. */
 int lwsb_set_tuning(lwsb_ctx *ctx, long long smem_limit, int cluster, int sweeps_per_pass);
+/* kernel variant knobs: frames between consecutive sweeps (0 = automatic, else >= Q) and the experimental
+ * tensor-memory producer/consumer variant of the strip kernel (0 = off, the default; 1 = on) */
+int lwsb_set_variant(lwsb_ctx *ctx, int sweep_lag, int tensor_memory);
 /* cycle accounting of cluster 0 in the last strip-kernel launch, summed over its CTAs: control lane {publish,
  * poll neighbours, TMA housekeeping}, compute warps {work, wait for the strip, wait for the neighbours, warps} */
-int lwsb_last_batch_cycles(lwsb_ctx *ctx, unsigned long long *out7);
+int lwsb_last_batch_cycles(lwsb_ctx *ctx, unsigned long long *out13); /* + 6 consumer-phase counters (TM kernels) */
 int lwsb_device_info(lwsb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, long long *hbm_bytes);
 /* per-utterance statistics of the resident batch (mean / max of |S|, lws.pyx:240) */
 int lwsb_get_stats(lwsb_ctx *ctx, double *mean_amp, double *max_amp);
@@ -150,7 +153,7 @@ int lwsb_get_stats(lwsb_ctx *ctx, double *mean_amp, double *max_amp);
  *    into (row, weight set, rframe, cframe, threshold index or -1). */
 int lwsb_debug_terms(const double *wr, const double *wi, int Q, int L, int fold, int rframe, int cframe, int p,
                      int max_terms, int *dr, int *dk, double *cr, double *ci);
-/*  - lwsb_debug_plan_strips: the plan the cluster strip kernel would use (same 11 numbers as
+/*  - lwsb_debug_plan_strips: the plan the cluster strip kernel would use (same 12 numbers as
  *    lwsb_last_batch_plan) for a shape and a shared-memory / SM budget; returns 0 when the generic kernel serves it. */
 int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, int maxT, int B, long long smem_limit,
                            int sm_count, int force_cluster, int max_sweeps, int *out9);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "lwsb_debug_terms": (_ci, [_dp, _dp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ip, _ip, _dp, _dp]),
     "lwsb_debug_plan_strips": (_ci, [_ci, _ci, _ci, _ci, _ci, _ci, _ll, _ci, _ci, _ci, _ip]),
     "lwsb_set_tuning": (_ci, [_vp, _ll, _ci, _ci]),
+    "lwsb_set_variant": (_ci, [_vp, _ci, _ci]),
     "lwsb_last_batch_cycles": (_ci, [_vp, ctypes.POINTER(ctypes.c_ulonglong)]),
     "lwsb_debug_online_chain_length": (_ll, [_ci, _ci, _ci]),
     "lwsb_debug_online_task": (_ci, [_ci, _ci, _ci, _ci, _ll, _ip, _ip, _ip, _ip, _ip]),
@@ -258,16 +259,20 @@ class Context(object):
     def set_tuning(self, smem_limit=0, cluster=0, sweeps_per_pass=0):
         self._c(lib().lwsb_set_tuning(self._h, int(smem_limit), int(cluster), int(sweeps_per_pass)))
 
+    def set_variant(self, sweep_lag=0, tensor_memory=0):
+        self._c(lib().lwsb_set_variant(self._h, int(sweep_lag), int(tensor_memory)))
+
     def last_batch_cycles(self):
-        out = (ctypes.c_ulonglong * 7)()
+        out = (ctypes.c_ulonglong * 13)()
         if self._c(lib().lwsb_last_batch_cycles(self._h, out)) != 1:
             return None
-        keys = ("ctrl_publish", "ctrl_poll", "ctrl_tma", "warp_work", "warp_wait_strip", "warp_wait_neighbours", "warps")
+        keys = ("ctrl_publish", "ctrl_poll", "ctrl_tma", "warp_work", "warp_wait_strip", "warp_wait_neighbours", "warps",
+                "c_setup", "c_own_terms", "c_wait_a", "c_chain_a", "c_wait_b", "c_chain_b")
         return dict(zip(keys, [int(x) for x in out]))
 
     def last_batch_plan(self):
         """dict describing the cluster strip plan of the last batch() call, or None (generic kernel)."""
-        out = (ctypes.c_int * 11)()
+        out = (ctypes.c_int * 12)()
         if self._c(lib().lwsb_last_batch_plan(self._h, out)) != 1:
             return None
         return dict(zip(PLAN_KEYS, list(out)))
@@ -302,11 +307,11 @@ def debug_terms(Wc, fold, rframe, cframe, p):
 
 
 PLAN_KEYS = ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots", "sweeps_per_pass", "ring_rows",
-             "ring_pitch", "threads", "smem_bytes", "sweep_lag", "sweep_fastest")
+             "ring_pitch", "threads", "smem_bytes", "sweep_lag", "sweep_fastest", "tensor_memory")
 
 
 def debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit=232448, sm_count=148, cluster=0, sweeps=0):
-    out = (ctypes.c_int * 11)()
+    out = (ctypes.c_int * 12)()
     if _check(lib().lwsb_debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit, sm_count, cluster, sweeps,
                                            out)) != 1:
         return None

@@ -65,6 +65,8 @@ struct lwsb_ctx {
     long long tune_smem = 0;               // tuning knobs (lwsb_set_tuning): shared-memory budget, cluster size,
     int tune_cluster = 0, tune_sweeps = 0; // sweeps per pass; 0 = automatic
     int tune_lag = 0;                      // frames between sweeps (env LWSB_STRIP_LAG only)
+    int tune_tm = 0;                       // tensor-memory producer/consumer kernel (env LWSB_STRIP_TM=1, lwsb_set_tuning2);
+                                           // off by default: measured slower than the single-warp pipeline
     StripPlan last_plan{};
     std::map<int, DevBuf> twiddles;        // exp(-2 pi i j / N) tables by N
     std::vector<void *> hptr;
@@ -182,6 +184,7 @@ extern "C" int lwsb_create(int device, void *stream, lwsb_ctx **out)
     if (const char *e2 = getenv("LWSB_STRIP_CLUSTER")) c->tune_cluster = atoi(e2);
     if (const char *e3 = getenv("LWSB_STRIP_SWEEPS")) c->tune_sweeps = atoi(e3);
     if (const char *e4 = getenv("LWSB_STRIP_LAG")) c->tune_lag = atoi(e4);
+    if (const char *e5 = getenv("LWSB_STRIP_TM")) c->tune_tm = atoi(e5);
     *out = c;
     return LWSB_OK;
 }
@@ -391,11 +394,11 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
                         plan_strips(c->Nreal, c->Q, c->L, iterations, c->maxT, c->B,
                                     c->tune_smem > 0 ? std::min((size_t)c->tune_smem, c->prop.sharedMemPerBlockOptin)
                                                      : c->prop.sharedMemPerBlockOptin,
-                                    c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps, c->tune_lag) &&
+                                    c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps, c->tune_lag, c->tune_tm) &&
                         c->P >= strips_min_pitch(c->Nreal, c->c0);
     if (strips) {
-        CU(c, c->status.reserve(128));
-        CU(c, cudaMemsetAsync(c->status.p, 0, 128, c->stream));
+        CU(c, c->status.reserve(256));
+        CU(c, cudaMemsetAsync(c->status.p, 0, 256, c->stream));
         if (int r = begin_compute(c)) return r;
         CU(c, launch_batch_strips(c->view(), c->w[LWSB_W].wr.data(), c->w[LWSB_W].wi.data(), fold,
                                   c->dthr.as<const double>(), c->max_amp.as<const double>(), iterations, pl,
@@ -674,7 +677,7 @@ extern "C" int lwsb_last_batch_cycles(lwsb_ctx *c, unsigned long long *out7)
     if (!out7) return fail(c, LWSB_ERR_ARG, "out7 is NULL");
     if (c->last_kernel != 1 || !c->status.p) return 0;
     if (int r = use_device(c)) return r;
-    CU(c, cudaMemcpyAsync(out7, c->status.as<char>() + 8, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(out7, c->status.as<char>() + 8, 13 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return 1;
 }
@@ -688,13 +691,21 @@ extern "C" int lwsb_set_tuning(lwsb_ctx *c, long long smem_limit, int cluster, i
     return LWSB_OK;
 }
 
+extern "C" int lwsb_set_variant(lwsb_ctx *c, int sweep_lag, int tensor_memory)
+{
+    CHECK_CTX(c);
+    if (sweep_lag < 0 || tensor_memory < 0 || tensor_memory > 1) return fail(c, LWSB_ERR_ARG, "bad variant values");
+    c->tune_lag = sweep_lag; c->tune_tm = tensor_memory;
+    return LWSB_OK;
+}
+
 extern "C" int lwsb_last_batch_plan(const lwsb_ctx *c, int *out9)
 {
     if (!c || !out9) return LWSB_ERR_ARG;
     if (c->last_kernel != 1) return 0;
     const StripPlan &p = c->last_plan;
-    const int v[11] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST};
-    for (int i = 0; i < 11; ++i) out9[i] = v[i];
+    const int v[12] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM};
+    for (int i = 0; i < 12; ++i) out9[i] = v[i];
     return 1;
 }
 
@@ -746,9 +757,9 @@ extern "C" int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, i
 {
     if (!out9) return LWSB_ERR_ARG;
     StripPlan p;
-    if (!plan_strips(Nreal, Q, L, iterations, maxT, B, (size_t)smem_limit, sm_count, &p, force_cluster, max_sweeps, 0)) return 0;
-    const int v[11] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST};
-    for (int i = 0; i < 11; ++i) out9[i] = v[i];
+    if (!plan_strips(Nreal, Q, L, iterations, maxT, B, (size_t)smem_limit, sm_count, &p, force_cluster, max_sweeps, 0, 0)) return 0;
+    const int v[12] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM};
+    for (int i = 0; i < 12; ++i) out9[i] = v[i];
     return 1;
 }
 

@@ -455,18 +455,200 @@ __device__ __forceinline__ void strip_update_block_pipelined(RingCell<Q> &cell, 
     }
 }
 
+// ---------------------------------------------------------------- tensor memory as a term-value scratch pad (TM kernels)
+// The register file cannot hold the 59 neighbour values of a bin for several bins at once, and shared memory is
+// full of ring rows, but the SM's 256 KB of tensor memory is idle in this (tensor-core free) kernel.  TMEM is
+// private to a lane quarter, and warps w and w+4 share a quarter: a PRODUCER warp (4..7) loads the neighbour
+// frames once per half block (two 14-bin windows per frame pair, kept in registers and reused by four bins),
+// forms the inter-frame term values of four bins and parks them in TMEM (tcgen05.st); its CONSUMER twin (0..3)
+// fetches them (tcgen05.ld) and runs the order-bound part: the additions in the reference's order, sqrt, divide,
+// commit.  The two warps sit on the same scheduler, so the producer's issue-bound stream fills the consumer's
+// dependency stalls.  Layout per lane: buffer h (half block) at columns [256h, 256h+256), bin b of the half at
+// +64b, term number n (in order of addition) at +4n: {re.lo, re.hi, im.lo, im.hi}.
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld64(uint32_t taddr, uint32_t *v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]),
+          "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]),
+          "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]),
+          "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr)
+        : "memory");
+}
+
+// position (in order of addition) of the first term of frame pair r for a bin of residue p, default-window mask
+template <int Q, int FOLD>
+__device__ __forceinline__ constexpr int tm_slot_base(int p, int r)
+{
+    // terms per frame pair: 1 + 5, except r = Q/2 with k in {0,1,2,4}: 4
+    int base = 0;
+    if (FOLD == LWSB_FOLD_Q4 && (p & 1)) { // order 1, 3, 2
+        if (r == 1) return 0;
+        if (r == 3) return 6;
+        return 12;
+    }
+    for (int q = 1; q < r; ++q) base += (2 * q == Q) ? 4 : 6;
+    return base;
+}
+template <int Q>
+__device__ __forceinline__ constexpr int tm_terms_per_bin()
+{
+    int n = 0;
+    for (int q = 1; q < Q; ++q) n += (2 * q == Q) ? 4 : 6;
+    return n; // 16 for Q = 4, 4 for Q = 2
+}
+
+// PRODUCER: term values of the four bins [4H, 4H+4) of the block for frame pair R_ (default mask), into TMEM
+template <int Q, int FOLD, int H, int R_>
+__device__ __forceinline__ void tm_produce_r(const unsigned char *ring, const unsigned *rowoff, int colbase, const StripW<Q> &w,
+                                             uint32_t tbuf)
+{
+    // windows: ring columns colbase - 5 .. colbase + 8 of frames m - R_ and m + R_
+    double2 wm[14], wp[14];
+    const double2 *rm = reinterpret_cast<const double2 *>(ring + rowoff[Q - 1 - R_]) + (colbase - SL);
+    const double2 *rp = reinterpret_cast<const double2 *>(ring + rowoff[Q - 1 + R_]) + (colbase - SL);
+#pragma unroll
+    for (int q = 0; q < 14; ++q) { wm[q] = rm[q]; wp[q] = rp[q]; }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        constexpr int dummy = 0; (void)dummy;
+        const int p = (4 * H + b) % Q;                  // compile-time after unrolling
+        const bool minus = FOLD == LWSB_FOLD_Q4 && (p & 1) && (R_ & 1);
+        const int slot0 = tm_slot_base<Q, FOLD>(p, R_);
+        double vr[6], vi[6];
+        int n = 0;
+        pair_value(w.wr[p][R_][0], w.wi[p][R_][0], wm[b + 5].x, wm[b + 5].y, wp[b + 5].x, wp[b + 5].y, vr[n], vi[n]);
+        ++n;
+#pragma unroll
+        for (int k = 1; k <= SL; ++k) {
+            if (!pat_has<Q, 1>(R_, k)) continue;
+            const double2 e1 = wm[b + 5 - k], e2 = wp[b + 5 + k], e3 = wp[b + 5 - k], e4 = wm[b + 5 + k];
+            double br, bi, cr, ci;
+            if (minus) {
+                br = __dsub_rn(e1.x, e2.x); bi = __dsub_rn(e1.y, e2.y);
+                cr = __dsub_rn(e3.x, e4.x); ci = __dsub_rn(e3.y, e4.y);
+            } else {
+                br = __dadd_rn(e1.x, e2.x); bi = __dadd_rn(e1.y, e2.y);
+                cr = __dadd_rn(e3.x, e4.x); ci = __dadd_rn(e3.y, e4.y);
+            }
+            pair_value(w.wr[p][R_][k], w.wi[p][R_][k], br, bi, cr, ci, vr[n], vi[n]);
+            ++n;
+        }
+        // two terms (8 words) per store
+        const uint32_t t0 = tbuf + (uint32_t)(64 * b + 4 * slot0);
+#pragma unroll
+        for (int q = 0; q + 1 < 6; q += 2) {
+            if (q >= n) break;
+            uint32_t x[8];
+            x[0] = (uint32_t)__double2loint(vr[q]); x[1] = (uint32_t)__double2hiint(vr[q]);
+            x[2] = (uint32_t)__double2loint(vi[q]); x[3] = (uint32_t)__double2hiint(vi[q]);
+            x[4] = (uint32_t)__double2loint(vr[q + 1]); x[5] = (uint32_t)__double2hiint(vr[q + 1]);
+            x[6] = (uint32_t)__double2loint(vi[q + 1]); x[7] = (uint32_t)__double2hiint(vi[q + 1]);
+            tm_st8(t0 + 4 * q, x);
+        }
+    }
+}
+
+// Work split of a task between its two warps (Q = 4): the PRODUCER forms the terms of the frame pairs r = 1 and 3
+// (12 of 16 terms), the CONSUMER those of r = 2 (4 terms) before it starts on the ordered sums -- roughly equal
+// instruction counts, so both warps of a scheduler stay busy.  Q = 2 has a single frame pair: producer only.
+template <int Q, int FOLD, int H, bool CONSUMER_SHARE>
+__device__ __forceinline__ void tm_produce_half(const unsigned char *ring, const unsigned *rowoff, int xb, const StripW<Q> &w,
+                                                uint32_t tlane)
+{
+    const int colbase = SL + SBK * xb + 4 * H;
+    const uint32_t tbuf = tlane + 256u * H;
+    if constexpr (Q == 4) {
+        if constexpr (CONSUMER_SHARE) tm_produce_r<Q, FOLD, H, 2>(ring, rowoff, colbase, w, tbuf);
+        else {
+            tm_produce_r<Q, FOLD, H, 1>(ring, rowoff, colbase, w, tbuf);
+            tm_produce_r<Q, FOLD, H, 3>(ring, rowoff, colbase, w, tbuf);
+        }
+    } else {
+        if constexpr (!CONSUMER_SHARE) {
+            if constexpr (Q > 1) tm_produce_r<Q, FOLD, H, 1>(ring, rowoff, colbase, w, tbuf);
+            if constexpr (Q > 2) tm_produce_r<Q, FOLD, H, 2>(ring, rowoff, colbase, w, tbuf);
+            if constexpr (Q > 3) tm_produce_r<Q, FOLD, H, 3>(ring, rowoff, colbase, w, tbuf);
+        }
+    }
+}
+
+// CONSUMER: the order-bound part of the four bins [4H, 4H+4): centre-frame term, the ordered sum, projection, commit
+template <int Q, int FOLD, int H, int B_>
+__device__ __forceinline__ void tm_consume_bins(const StripW<Q> &w, const BlockCtx &bc, const double *amp, unsigned active,
+                                                uint32_t tbuf, double2 *newv, unsigned &committed)
+{
+    if constexpr (B_ < 4) {
+        constexpr int I = 4 * H + B_;
+        constexpr int P = I % Q;
+        constexpr int NT = tm_terms_per_bin<Q>();
+        uint32_t x[64];
+        tm_ld64(tbuf + 64u * B_, x);
+        double2 *own = reinterpret_cast<double2 *>(bc.ring + bc.ownoff);
+        const int col = SL + SBK * bc.xb + I;
+        // centre-frame term (default mask: k = 1 only); sees the bin updated just before (lwslib.cpp:169-182)
+        const double2 b = own[col - 1], c = own[col + 1];
+        double tr, ti;
+        pair_value(w.wr[P][0][1], w.wi[P][0][1], b.x, b.y, c.x, c.y, tr, ti);
+        tr = __dadd_rn(0.0, tr); ti = __dadd_rn(0.0, ti);
+        tm_wait_ld();
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            tr = __dadd_rn(tr, __hiloint2double((int)x[4 * n + 1], (int)x[4 * n]));
+            ti = __dadd_rn(ti, __hiloint2double((int)x[4 * n + 3], (int)x[4 * n + 2]));
+        }
+        double2 val;
+        const bool ok = x_project(tr, ti, amp[I], val) && ((active >> I) & 1u);
+        const int n = bc.n0 + I;
+        int mcol = col;
+        if (bc.first_strip && n >= 1 && n <= SL) mcol = SL - n;
+        else if (n >= bc.Nreal - 1 - SL && n <= bc.Nreal - 2) mcol = SL + 2 * (bc.Nreal - 1) - n - bc.b0;
+        if (ok) {
+            own[col] = val;
+            own[mcol] = make_double2(val.x, mcol == col ? val.y : -val.y);
+            committed |= 1u << I;
+        }
+        newv[I] = val;
+        tm_consume_bins<Q, FOLD, H, B_ + 1>(w, bc, amp, active, tbuf, newv, committed);
+    }
+}
+
 // ---------------------------------------------------------------- the kernel
-template <int Q, int FOLD, int PAT>
-__global__ void __launch_bounds__(256, 1)
+// TM = true: 8 warps, 0..3 consume and 4..7 produce (through tensor memory); needs the default mask
+template <int Q, int FOLD, int PAT, bool TM>
+__global__ void __maxnreg__(255)
 k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ StripW<Q> w)
 {
+    static_assert(!TM || (PAT == 1 && FOLD != LWSB_FOLD_ANY && Q <= 4), "the TMEM layout is laid out for the folded default-mask terms");
     cg::cluster_group cluster = cg::this_cluster();
     const int C = prm.C;
     const int c = (int)cluster.block_rank();
     const int cid = blockIdx.x / C, ncl = gridDim.x / C;
     const int tid = threadIdx.x;
-    const int nct = (int)blockDim.x - 32; // compute threads; the last warp is the control warp
-    const bool is_ctrl = tid >= nct;
+    // control duties (neighbour hand-shake, TMA traffic): a warp of its own, or -- TM kernels, which need two
+    // warps per scheduler and all their registers -- lane 0 of the last producer warp
+    const int nct = TM ? (int)blockDim.x : (int)blockDim.x - 32; // task threads
+    const bool is_ctrl = !TM && tid >= nct;
+    const bool ctl = TM ? (tid == (int)blockDim.x - 32) : (is_ctrl && (tid & 31) == 0); // the one thread doing them
     const int lane = tid & 31;
     const LwsbView &v = prm.v;
     const int NBr = prm.NBr, NBV = prm.NBV, NS = prm.NS, G = prm.G, R = prm.R, pitch = prm.pitch;
@@ -497,11 +679,28 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
     // per-thread slot: frame residue j, sweep slot g
     // thread order: sweep slot fastest (lanes of a quarter-warp sit QS rows apart: conflict free for odd QS) or
     // frame slot fastest (lanes on consecutive frames); the planner picks the one with fewer bank conflicts
-    const int j = prm.GFAST ? tid / G : tid % NS, g = prm.GFAST ? tid % G : tid / NS;
+    const int tix = TM ? (tid & 127) : tid;            // task index: producer lane l of warp w+4 serves consumer lane l of warp w
+    const bool is_producer = TM && tid >= 128 && !is_ctrl;
+    const int j = prm.GFAST ? tix / G : tix % NS, g = prm.GFAST ? tix % G : tix / NS;
     const bool has_slot = !is_ctrl && j < NS && g < G;
+
+    // tensor memory: all 512 columns of this SM (one CTA per SM), base address through shared memory
+    __shared__ uint32_t tm_base_smem;
+    uint32_t tlane = 0;
+    if constexpr (TM) {
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tm_base_smem)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        tm_fence_before();
+        __syncthreads();
+        tm_fence_after();
+        tlane = tm_base_smem + ((uint32_t)((tid >> 5) & 3) << 21); // lane field (bits 31:16) = 32 * quarter
+    }
 
     bool mbar_live = false;
     long long tm_publish = 0, tm_poll = 0, tm_house = 0, tm_work = 0, tm_waitA = 0, tm_waitB = 0; // cycle counters (status[2..])
+    long long ph[6] = {0, 0, 0, 0, 0, 0}; // consumer phases of the TM kernels: set-up, own terms, wait A, chain A, wait B, chain B
     for (int u = cid; u < v.B; u += ncl) {
         const int T = v.T[u];
         const int Tp = T + 2 * (Q - 1);
@@ -524,9 +723,9 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
             const double thr = (has_slot && g < Gp) ? __dmul_rn(prm.thr[act[pass * G + g]], mean) : 0.0; // lws.pyx:245
 
             // ---- pass prologue: previous pass fully written back everywhere, ring (re)initialised
-            if (is_ctrl && lane == 0) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
+            if (ctl) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
             cluster.sync();
-            if (is_ctrl && lane == 0) {
+            if (ctl) {
                 if (!mbar_live) {
                     for (int s = 0; s < R; ++s) mbar_init(&mbar[s], 1);
                     fence_mbar_init();
@@ -542,80 +741,189 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
             }
             cluster.sync();
 
+            // ---- control actions (executed by the thread `ctl` only)
+            auto poll = [&](int t) { // conditions for macro-step t (DESIGN.md "strip hand-shake")
+                if (c > 0) {
+                    const unsigned need = (unsigned)min(t + NBr, nsteps);
+                    unsigned spins = 0;
+                    while (ld_acquire_cluster(&flags[0]) < need) {
+                        __nanosleep(32);
+                        if (!keep_waiting(spins, prm.status, 0x10000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
+                    }
+                }
+                if (c < C - 1 && t - NBr > 0) {
+                    const unsigned need = (unsigned)(t - NBr);
+                    unsigned spins = 0;
+                    while (ld_acquire_cluster(&flags[1]) < need) {
+                        __nanosleep(32);
+                        if (!keep_waiting(spins, prm.status, 0x20000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
+                    }
+                }
+            };
+            // publish first: the neighbours' next macro-step waits for this one.  (Polling for step t+1 before
+            // publishing step t would dead-lock: in lock step the neighbour's matching step finishes only after
+            // it has seen this strip's step t.)
+            auto publish = [&](int done) {
+                if (flag_at_left) st_release_cluster(flag_at_left, (unsigned)done);
+                if (flag_at_right) st_release_cluster(flag_at_right, (unsigned)done);
+            };
+            // TMA traffic after macro-step t, overlapped with macro-step t + 1: nothing here touches a row in use
+            auto housekeeping = [&](int t) {
+                if (((t + 1) & 1) == 0) { // next frame into the slot freed longest ago
+                    const int e = (t + 1) / 2 + 2 * (Q - 1) + SLEAD;
+                    if (e < Tp) {
+                        tma_store_wait_read(); // bulk stores issued a macro-step or more ago: long finished reading
+                        fence_proxy_async();
+                        mbar_expect_tx(&mbar[e % R], load_bytes);
+                        tma_load_row(ring + (size_t)(e % R) * rowbytes, v.E + (grow0 + e) * P + gcol0, load_bytes, &mbar[e % R]);
+                    }
+                }
+                const int tf = t - (nb_my - 1); // frame whose last sweep of this pass finished its last real block in step t
+                if (nb_my > 0 && tf >= 0 && (tf & 1) == 0) {
+                    const int m = tf / 2 - QS * (Gp - 1);
+                    if (m >= 0 && m < T) {
+                        const int e = m + Q - 1;
+                        fence_proxy_async();
+                        tma_store_row(v.E + (grow0 + e) * P + gcol0 + wb_lo,
+                                      ring + (size_t)(e % R) * rowbytes + (size_t)wb_lo * 16u, (unsigned)(wb_hi - wb_lo) * 16u);
+                    }
+                }
+            };
+            // Slot s received Tp/R (+1) rows in this pass, one mbarrier phase each.  The waits address phases by
+            // parity counted from the start of the pass, so slots that saw an odd number of phases get one empty
+            // phase: every barrier starts the next pass at parity 0 again.
+            auto fix_parity = [&]() {
+                for (int s = 0; s < R; ++s)
+                    if ((Tp / R + (s < Tp % R ? 1 : 0)) & 1) mbar_arrive(&mbar[s]);
+            };
+
             if (is_ctrl) {
-                // ================= control warp: neighbour hand-shake, TMA traffic =================
-                auto poll = [&](int t) { // conditions for macro-step t (DESIGN.md "strip hand-shake")
-                    if (lane != 0) return;
-                    if (c > 0) {
-                        const unsigned need = (unsigned)min(t + NBr, nsteps);
-                        unsigned spins = 0;
-                        while (ld_acquire_cluster(&flags[0]) < need) {
-                            __nanosleep(32); // the control warp shares an issue port with a compute warp
-                            if (!keep_waiting(spins, prm.status, 0x10000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
-                        }
-                    }
-                    if (c < C - 1 && t - NBr > 0) {
-                        const unsigned need = (unsigned)(t - NBr);
-                        unsigned spins = 0;
-                        while (ld_acquire_cluster(&flags[1]) < need) {
-                            __nanosleep(32);
-                            if (!keep_waiting(spins, prm.status, 0x20000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
-                        }
-                    }
-                };
-                poll(0);
+                // ================= control warp (kernels without tensor memory) =================
+                if (ctl) poll(0);
+                __syncwarp();
                 cta_sync(); // releases the compute warps into macro-step 0
                 for (int t = 0; t < nsteps; ++t) {
                     cta_sync(); // macro-step t computed by every thread of the strip
                     const long long c0 = clock64();
-                    if (lane == 0) {
-                        // publish first: the neighbours' next macro-step waits for this one.  (Polling for
-                        // step t+1 before publishing step t would dead-lock: in lock step the neighbour's
-                        // matching step finishes only after it has seen this strip's step t.)
-                        const unsigned done = (unsigned)(t + 1);
-                        if (flag_at_left) st_release_cluster(flag_at_left, done);
-                        if (flag_at_right) st_release_cluster(flag_at_right, done);
-                    }
+                    if (ctl) publish(t + 1);
                     const long long c1 = clock64();
-                    if (t + 1 < nsteps) poll(t + 1);
+                    if (ctl && t + 1 < nsteps) poll(t + 1);
                     __syncwarp();
                     const long long c2 = clock64();
                     cta_sync(); // releases the compute warps into macro-step t + 1
-                    // TMA traffic, overlapped with macro-step t + 1: nothing below touches a row in use
-                    if (lane == 0) {
-                        // frame whose last sweep of this pass finished its last real block in step t
-                        const int tf = t - (nb_my - 1);
-                        if (nb_my > 0 && tf >= 0 && (tf & 1) == 0) {
-                            const int m = tf / 2 - QS * (Gp - 1);
-                            if (m >= 0 && m < T) {
-                                const int e = m + Q - 1;
-                                fence_proxy_async();
-                                tma_store_row(v.E + (grow0 + e) * P + gcol0 + wb_lo,
-                                              ring + (size_t)(e % R) * rowbytes + (size_t)wb_lo * 16u, (unsigned)(wb_hi - wb_lo) * 16u);
-                            }
-                        }
-                        // next frame into the slot freed longest ago
-                        if (((t + 1) & 1) == 0) {
-                            const int e = (t + 1) / 2 + 2 * (Q - 1) + SLEAD;
-                            if (e < Tp) {
-                                tma_store_wait_read();
-                                fence_proxy_async();
-                                mbar_expect_tx(&mbar[e % R], load_bytes);
-                                tma_load_row(ring + (size_t)(e % R) * rowbytes, v.E + (grow0 + e) * P + gcol0, load_bytes, &mbar[e % R]);
-                            }
-                        }
-                    }
+                    if (ctl) housekeeping(t);
                     __syncwarp();
                     tm_publish += c1 - c0; tm_poll += c2 - c1; tm_house += clock64() - c2;
                 }
-                // Slot s received Tp/R (+1) rows in this pass, one mbarrier phase each.  The waits address
-                // phases by parity counted from the start of the pass, so slots that saw an odd number of
-                // phases get one empty phase: every barrier starts the next pass at parity 0 again.
-                if (lane == 0)
-                    for (int s = 0; s < R; ++s)
-                        if ((Tp / R + (s < Tp % R ? 1 : 0)) & 1) mbar_arrive(&mbar[s]);
+                if (ctl) fix_parity();
             } else {
-                // ================= compute warps =================
+                // ================= task warps =================
+                if constexpr (TM) {
+                    int xb = -2 * j;
+                    int m = j - QS * g;
+                    if (ctl) poll(0);
+                    __syncwarp();
+                    cta_sync(); // macro-step 0 verified
+                    for (int t = 0; t < nsteps; ++t) {
+                        const long long k0 = clock64();
+                        if ((t & 1) == 0) {
+                            const int k = t >> 1;
+                            const int e_lo = k == 0 ? 0 : k + 2 * (Q - 1), e_hi = k + 2 * (Q - 1);
+                            for (int e = e_lo; e <= e_hi && e < Tp; ++e) {
+                                unsigned spins = 0;
+                                while (!mbar_try_wait(&mbar[e % R], (unsigned)((e / R) & 1)))
+                                    if (!keep_waiting(spins, prm.status, 0x30000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
+                            }
+                        }
+                        const bool valid = has_slot && g < Gp && xb >= 0 && xb < nb_my && m >= 0 && m < T;
+                        const int e = valid ? m + Q - 1 : Q - 1;
+                        const int xbv = valid ? xb : 0;
+                        const int n0 = b0 + SBK * xbv;
+                        double amp[SBK];
+                        unsigned active = 0;
+                        if (valid) {
+                            const double2 *ap = reinterpret_cast<const double2 *>(v.A + (grow0 + e) * P + v.c0 + n0);
+#pragma unroll
+                            for (int q = 0; q < SBK / 2; ++q) {
+                                const double2 a2 = __ldg(ap + q);
+                                amp[2 * q] = a2.x; amp[2 * q + 1] = a2.y;
+                            }
+#pragma unroll
+                            for (int i = 0; i < SBK; ++i)
+                                if (n0 + i < Nreal && amp[i] > thr) active |= 1u << i;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < SBK; ++i) amp[i] = 0.0;
+                        }
+                        // the tcgen05 operations are warp collectives: the producer / consumer pair takes the same
+                        // decision (same task indices, same amplitudes), lanes without work run on harmless data
+                        const long long q0 = clock64();
+                        ph[0] += q0 - k0;
+                        if (__any_sync(0xffffffffu, active != 0)) {
+                            unsigned rowoff[2 * Q - 1];
+                            const int es = e % R;
+#pragma unroll
+                            for (int d = 0; d < 2 * Q - 1; ++d) {
+                                int sl = es + d - (Q - 1);
+                                sl = sl < 0 ? sl + R : (sl >= R ? sl - R : sl);
+                                rowoff[d] = (unsigned)sl * rowbytes;
+                            }
+                            const int bar0 = 2 + 2 * ((tid >> 5) & 3);
+                            if (is_producer) {
+                                tm_produce_half<Q, FOLD, 0, false>(ring, rowoff, xbv, w, tlane);
+                                tm_wait_st(); tm_fence_before(); pair_arrive(bar0);
+                                tm_produce_half<Q, FOLD, 1, false>(ring, rowoff, xbv, w, tlane);
+                                tm_wait_st(); tm_fence_before(); pair_arrive(bar0 + 1);
+                            } else {
+                                BlockCtx bc;
+                                bc.ring = ring; bc.ring_left = ring_left; bc.ring_right = ring_right;
+                                bc.ownoff = rowoff[Q - 1]; bc.xb = xbv; bc.n0 = n0; bc.b0 = b0;
+                                bc.Nreal = Nreal; bc.NBr = NBr; bc.first_strip = (c == 0);
+                                double2 newv[SBK];
+                                unsigned committed = 0;
+                                // the consumer's share of the term values, then the order-bound part
+                                tm_produce_half<Q, FOLD, 0, true>(ring, rowoff, xbv, w, tlane);
+                                tm_produce_half<Q, FOLD, 1, true>(ring, rowoff, xbv, w, tlane);
+                                tm_wait_st();
+                                const long long q1 = clock64();
+                                pair_sync(bar0); tm_fence_after();
+                                const long long q2 = clock64();
+                                tm_consume_bins<Q, FOLD, 0, 0>(w, bc, amp, active, tlane, newv, committed);
+                                const long long q3 = clock64();
+                                pair_sync(bar0 + 1); tm_fence_after();
+                                const long long q4 = clock64();
+                                tm_consume_bins<Q, FOLD, 1, 0>(w, bc, amp, active, tlane + 256u, newv, committed);
+                                const long long q5 = clock64();
+                                ph[1] += q1 - q0; ph[2] += q2 - q1; ph[3] += q3 - q2; ph[4] += q4 - q3; ph[5] += q5 - q4;
+                                if (bc.xb == 0 && ring_left) {
+                                    double2 *dst = reinterpret_cast<double2 *>(ring_left + bc.ownoff) + SL + SBK * NBr;
+#pragma unroll
+                                    for (int i = 0; i < SL; ++i)
+                                        if ((committed >> i) & 1u) dst[i] = newv[i];
+                                }
+                                if (bc.xb == NBr - 1 && ring_right) {
+                                    double2 *dst = reinterpret_cast<double2 *>(ring_right + bc.ownoff);
+#pragma unroll
+                                    for (int i = SBK - SL; i < SBK; ++i)
+                                        if ((committed >> i) & 1u) dst[i - (SBK - SL)] = newv[i];
+                                }
+                            }
+                        }
+                        const long long k1 = clock64();
+                        cta_sync(); // macro-step t done
+                        if (++xb == NBV) { xb = 0; m += NS; }
+                        const long long k2 = clock64();
+                        if (ctl) { publish(t + 1); if (t + 1 < nsteps) poll(t + 1); }
+                        __syncwarp();
+                        cta_sync(); // neighbours ready for macro-step t + 1
+                        const long long k3 = clock64();
+                        if (ctl) housekeeping(t);
+                        __syncwarp();
+                        if (is_producer) { tm_publish += k1 - k0; tm_poll += k2 - k1; tm_house += k3 - k2; }
+                        else { tm_work += k1 - k0; tm_waitA += k2 - k1; tm_waitB += k3 - k2; }
+                    }
+                    if (ctl) fix_parity();
+                } else {
                 int xb = -2 * j;          // block index; negative while the slot has not started
                 int m = j - QS * g;       // frame of the slot
                 cta_sync();               // control warp has verified macro-step 0
@@ -671,23 +979,28 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                     cta_sync(); // neighbours ready for macro-step t + 1
                     tm_work += k1 - k0; tm_waitA += k2 - k1; tm_waitB += clock64() - k2;
                 }
+                }
             }
         }
         // ---- utterance epilogue: everything written back before the ring is reused
-        if (is_ctrl && lane == 0) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
+        if (ctl) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
     }
     // cycle accounting of cluster 0 (introspection: lwsb_last_batch_cycles): control lane and one lane per compute warp
     if (cid == 0 && lane == 0) {
         unsigned long long *acc = reinterpret_cast<unsigned long long *>(prm.status + 2);
-        if (is_ctrl) {
+        if (is_ctrl || is_producer) { // control warp, or (TM kernels) producer warps: work / wait strip / wait neighbours
             atomicAdd(acc + 0, (unsigned long long)tm_publish); atomicAdd(acc + 1, (unsigned long long)tm_poll);
             atomicAdd(acc + 2, (unsigned long long)tm_house);
         } else {
             atomicAdd(acc + 3, (unsigned long long)tm_work); atomicAdd(acc + 4, (unsigned long long)tm_waitA);
             atomicAdd(acc + 5, (unsigned long long)tm_waitB); atomicAdd(acc + 6, 1ull);
+            for (int q = 0; q < 6; ++q) atomicAdd(acc + 7 + q, (unsigned long long)ph[q]);
         }
     }
     cluster.sync(); // no CTA leaves while a neighbour may still address its shared memory
+    if constexpr (TM) {
+        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base_smem) : "memory");
+    }
 }
 
 } // namespace
@@ -695,10 +1008,10 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
 // ---------------------------------------------------------------- host side
 namespace {
 
-template <int Q, int FOLD, int PAT>
+template <int Q, int FOLD, int PAT, bool TM>
 cudaError_t launch_strips_t(const StripParams &prm, const StripW<Q> &w, const StripPlan &pl, int B, cudaStream_t s)
 {
-    auto kern = k_batch_strips<Q, FOLD, PAT>;
+    auto kern = k_batch_strips<Q, FOLD, PAT, TM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
     if (e != cudaSuccess) return e;
     if (pl.C > 8) {
@@ -706,7 +1019,7 @@ cudaError_t launch_strips_t(const StripParams &prm, const StripW<Q> &w, const St
         if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(pl.nthreads);
+    cfg.blockDim = dim3(TM ? 256 : pl.nthreads);
     cfg.dynamicSmemBytes = pl.smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -745,17 +1058,24 @@ cudaError_t launch_strips_q(const StripParams &prm, const double *wr, const doub
             for (int k = (r == 0 ? 1 : 0); k <= SL; ++k)
                 if (pat_has<Q, 1>(r, k) != (((w.flag[p][r] >> k) & 1u) != 0)) { def = false; break; }
     if constexpr (Q <= 4) {
-        if (fold == LWSB_FOLD_ANY) return launch_strips_t<Q, LWSB_FOLD_ANY, 0>(prm, w, pl, B, s);
+        if (fold == LWSB_FOLD_ANY) return launch_strips_t<Q, LWSB_FOLD_ANY, 0, false>(prm, w, pl, B, s);
+        const bool tm = def && pl.TM && pl.NS * pl.G <= 128;
         if constexpr (Q == 4) {
-            if (fold == LWSB_FOLD_Q4)
-                return def ? launch_strips_t<4, LWSB_FOLD_Q4, 1>(prm, w, pl, B, s) : launch_strips_t<4, LWSB_FOLD_Q4, 0>(prm, w, pl, B, s);
+            if (fold == LWSB_FOLD_Q4) {
+                if (tm) return launch_strips_t<4, LWSB_FOLD_Q4, 1, true>(prm, w, pl, B, s);
+                return def ? launch_strips_t<4, LWSB_FOLD_Q4, 1, false>(prm, w, pl, B, s)
+                           : launch_strips_t<4, LWSB_FOLD_Q4, 0, false>(prm, w, pl, B, s);
+            }
         }
         if constexpr (Q == 2) {
-            if (fold == LWSB_FOLD_Q2)
-                return def ? launch_strips_t<2, LWSB_FOLD_Q2, 1>(prm, w, pl, B, s) : launch_strips_t<2, LWSB_FOLD_Q2, 0>(prm, w, pl, B, s);
+            if (fold == LWSB_FOLD_Q2) {
+                if (tm) return launch_strips_t<2, LWSB_FOLD_Q2, 1, true>(prm, w, pl, B, s);
+                return def ? launch_strips_t<2, LWSB_FOLD_Q2, 1, false>(prm, w, pl, B, s)
+                           : launch_strips_t<2, LWSB_FOLD_Q2, 0, false>(prm, w, pl, B, s);
+            }
         }
     } else {
-        if (fold == LWSB_FOLD_ANY) return launch_strips_t<Q, LWSB_FOLD_ANY, 0>(prm, w, pl, B, s);
+        if (fold == LWSB_FOLD_ANY) return launch_strips_t<Q, LWSB_FOLD_ANY, 0, false>(prm, w, pl, B, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -765,7 +1085,7 @@ cudaError_t launch_strips_q(const StripParams &prm, const double *wr, const doub
 // Chooses cluster size, strip width and sweeps per pass.  Returns false when the shape is not
 // served by this kernel (the generic kernel takes over).
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
-                 int force_cluster, int max_sweeps, int force_lag)
+                 int force_cluster, int max_sweeps, int force_lag, int use_tm)
 {
     if (L != SL || !(Q == 2 || Q == 4 || Q == 8) || iters < 1) return false;
     const int nbt = (Nreal + SBK - 1) / SBK; // blocks holding real bins
@@ -782,7 +1102,7 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
         int pitch = SBK * NBr + 2 * SL;
         if ((pitch & 1) == 0) ++pitch; // odd pitch: conflict-free 128-bit accesses across a warp's rows
         const size_t rowbytes = (size_t)pitch * 16;
-        const size_t fixed = 64 + 16 + (size_t)(iters + 8) * sizeof(int) + 256;
+        const size_t fixed = 64 + 16 + (size_t)(iters + 8) * sizeof(int) + 256 + 256; // flags, sweep list, alignment, static shared memory of the kernel
         if (smem_limit < fixed + rowbytes * 8) continue;
         const int Rmax = (int)((smem_limit - fixed) / (rowbytes + 8));
         const int ncl = std::max(1, (sm_count * 9 / 10) / C); // GPC packing loses a few SMs to clusters
@@ -791,7 +1111,8 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
         for (int QS = Q; QS <= Q + 1; ++QS) {
             if (Rmax < 2 * Q + SLEAD + NS) continue;
             int Gmax = (Rmax - 2 * Q - SLEAD - NS) / QS + 1;
-            Gmax = std::min(Gmax, (256 - 32) / NS);
+            const bool tm = use_tm != 0 && Q <= 4; // producer / consumer warps through tensor memory: 128 tasks per CTA
+            Gmax = std::min(Gmax, (tm ? 128 : 256 - 32) / NS);
             Gmax = std::min(Gmax, iters);
             if (max_sweeps > 0) Gmax = std::min(Gmax, max_sweeps);
             for (int G = Gmax; G >= 1 && G > Gmax - 8; --G) {
@@ -817,7 +1138,7 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                 const double cost = rounds * npass * (steps * (15000.0 + 900.0 * f * warps + (C > 1 ? 2500.0 * (C > 2 ? 1.0 : 0.5) : 0.0)) + 60000.0);
                 if (!found || cost < best) {
                     found = true; best = cost;
-                    out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast;
+                    out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast; out->TM = tm ? 1 : 0;
                     out->R = QS * (G - 1) + 2 * Q + SLEAD + NS;
                     out->nthreads = (NS * G + 31) / 32 * 32 + 32;
                     out->smem_bytes = (int)(fixed + (size_t)out->R * (rowbytes + 8));

@@ -288,3 +288,26 @@ def test_generic_and_strip_kernels_agree(gpu):
     a = gpu.batch_lws(A, p.W, thr)
     b = gpu.batch_lws(A, p.W, thr, flags=_native.FORCE_GENERIC)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("fs,hop,n,its,cluster,lag", [(512, 128, 9000, 9, 2, 0), (512, 128, 9000, 9, 4, 5), (1024, 256, 30000, 12, 8, 0),
+                                                      (128, 64, 9000, 10, 1, 0), (128, 64, 9000, 10, 2, 3)])
+def test_strip_kernel_tensor_memory_variant(gpu, oracle, fs, hop, n, its, cluster, lag):
+    """The experimental producer / consumer variant (term values handed from warp w+4 to warp w through
+    tensor memory, tcgen05.st / tcgen05.ld) and forced sweep lags: same bits."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(fs, hop), gpu.lws(fs, hop)
+    A = np.abs(po.stft(make_signal("tonal", 4, n)))
+    try:
+        ctx.set_tuning(0, cluster, 0)
+        ctx.set_variant(lag, 1)
+        for thr in (np.zeros(its), gpu.get_thresholds(its, 2.0, 0.1, 1)):
+            Y = pg.batch_lws(A, thresholds=thr)
+            plan = ctx.last_batch_plan()
+            assert plan is not None and plan["tensor_memory"] == 1 and plan["cluster"] == cluster
+            assert lag == 0 or plan["sweep_lag"] == lag
+            _close(Y, po.batch_lws(A, thresholds=thr), "tensor-memory variant %s" % (plan,))
+    finally:
+        ctx.set_tuning(0, 0, 0)
+        ctx.set_variant(0, 0)

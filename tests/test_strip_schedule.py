@@ -211,7 +211,7 @@ def test_planner_properties():
                         assert (C - 1) * NBr * SBK <= Nreal - 1 - SL           # mirror zone inside the last strip
                         assert R >= pl["sweep_lag"] * (G - 1) + 2 * Q + SLEAD + NS and 1 <= G <= iters and pl["sweep_lag"] >= Q
                         assert pl["ring_pitch"] % 2 == 1 and pl["ring_pitch"] >= SBK * NBr + 2 * SL
-                        assert pl["smem_bytes"] <= smem and pl["threads"] <= 256 and pl["threads"] >= NS * G + 32
+                        assert pl["smem_bytes"] <= smem and pl["threads"] <= 256 and pl["threads"] >= NS * G + 32 and (not pl["tensor_memory"] or NS * G <= 128)
                         assert R * pl["ring_pitch"] * 16 + R * 8 + 32 + 4 * iters <= pl["smem_bytes"]
     assert _native.debug_plan_strips(513, 3, 5, 10, 100, 1) is None     # Q must divide the block size
     assert _native.debug_plan_strips(513, 4, 7, 10, 100, 1) is None     # L is fixed at 5
