@@ -389,9 +389,25 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
     if (int r = use_device(c)) return r;
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
     const int fold = fold_for(c->Q, flags);
+    // sweeps whose threshold is not below max|S| cannot move a bin (lwslib.cpp:295-296): the strip kernel drops
+    // them, and the plan is sized for the number that remain (largest over the batch)
+    int active = iterations;
+    if (!(flags & LWSB_FORCE_GENERIC)) {
+        std::vector<double> mean(c->B), mx(c->B);
+        CU(c, cudaMemcpyAsync(mean.data(), c->mean_amp.p, c->B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(mx.data(), c->max_amp.p, c->B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        active = 0;
+        for (int b = 0; b < c->B; ++b) {
+            int n = 0;
+            for (int i = 0; i < iterations; ++i) n += (thresholds[i] * mean[b] < mx[b]) ? 1 : 0;
+            active = std::max(active, n);
+        }
+        active = std::max(active, 1);
+    }
     StripPlan pl;
     const bool strips = !(flags & LWSB_FORCE_GENERIC) &&
-                        plan_strips(c->Nreal, c->Q, c->L, iterations, c->maxT, c->B,
+                        plan_strips(c->Nreal, c->Q, c->L, active, c->maxT, c->B,
                                     c->tune_smem > 0 ? std::min((size_t)c->tune_smem, c->prop.sharedMemPerBlockOptin)
                                                      : c->prop.sharedMemPerBlockOptin,
                                     c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps, c->tune_lag, c->tune_tm) &&

@@ -1134,8 +1134,12 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                 if (force_lag > 0 && QS != force_lag) continue;
                 const int npass = (iters + G - 1) / G;
                 const double steps = 2.0 * (maxT + QS * G) + NBV + (C - 1) * NBr;
-                const double warps = NS * G / 32.0;
-                const double cost = rounds * npass * (steps * (15000.0 + 900.0 * f * warps + (C > 1 ? 2500.0 * (C > 2 ? 1.0 : 0.5) : 0.0)) + 60000.0);
+                // Cost model fitted on B200: a macro-step costs ~15k cycles of dependent
+                // fp64 latency plus ~1.1k per compute warp and shared-memory wavefront factor (measured over
+                // cluster sizes 2-8, 4-6 warps, conflict factors 1.0-2.0); a pass adds a fixed prologue.
+                const int cwarps = (NS * G + 31) / 32;
+                const double t_step = 15000.0 + 1100.0 * cwarps * f + (C > 2 ? 800.0 : 0.0);
+                const double cost = rounds * npass * (steps * t_step + 60000.0);
                 if (!found || cost < best) {
                     found = true; best = cost;
                     out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast; out->TM = tm ? 1 : 0;
