@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblws_b200.so")
-SOURCES = ["api.cu", "kernels_generic.cu", "kernels_batch.cu", "kernels_fft.cu"]
+SOURCES = ["api.cu", "kernels_generic.cu", "kernels_batch.cu", "kernels_online.cu", "kernels_fft.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--shared", "-cudart", "static",

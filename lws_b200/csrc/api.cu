@@ -476,10 +476,30 @@ extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
     const LwsbW w3[3] = {c->devw(LWSB_W), c->devw(LWSB_W_AI), c->devw(LWSB_W_AF)};
     if (int r = begin_compute(c)) return r;
-    launch_online_generic(c->view(), w3, fold_for(c->Q, flags), c->dthr.as<const double>(), iterations, look_ahead,
-                          c->stream);
+    bool ring = false;
+    if (!(flags & LWSB_FORCE_GENERIC)) {
+        cudaError_t e = cudaSuccess;
+        CU(c, c->status.reserve(256));
+        CU(c, cudaMemsetAsync(c->status.p, 0, 256, c->stream));
+        const double *wrh[3] = {c->w[0].wr.data(), c->w[1].wr.data(), c->w[2].wr.data()};
+        const double *wih[3] = {c->w[0].wi.data(), c->w[1].wi.data(), c->w[2].wi.data()};
+        ring = launch_online_ring(c->view(), wrh, wih, fold_for(c->Q, flags), c->dthr.as<const double>(), iterations,
+                                  look_ahead, c->T.data(), c->prop.sharedMemPerBlockOptin, c->status.as<unsigned>(),
+                                  c->stream, &e);
+        CU(c, e);
+    }
+    if (!ring)
+        launch_online_generic(c->view(), w3, fold_for(c->Q, flags), c->dthr.as<const double>(), iterations, look_ahead,
+                              c->stream);
     c->launches += 1;
-    return end_compute(c);
+    if (int r = end_compute(c)) return r;
+    if (ring) {
+        unsigned st = 0;
+        CU(c, cudaMemcpyAsync(&st, c->status.p, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (st != 0) return fail(c, LWSB_ERR_CUDA, "online kernel: shared-memory ring undersized (internal error)");
+    }
+    return LWSB_OK;
 }
 
 // Between two chained stages the reference crops and re-extends (lws.pyx:256 then 235-240 of the

@@ -25,6 +25,10 @@ void launch_sweeps_generic(const LwsbView &v, const LwsbW &w, int fold, int rfra
                            int iters, cudaStream_t s);
 void launch_online_generic(const LwsbView &v, const LwsbW *w3, int fold, const double *thr, int iters, int LA,
                            cudaStream_t s);
+// kernels_online.cu
+bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const double *const *wi_host, int fold,
+                        const double *thr, int iters, int LA, const int *T_host, size_t smem_limit, unsigned *status,
+                        cudaStream_t s, cudaError_t *err);
 void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, int iters, cudaStream_t s);
 
 // kernels_batch.cu

@@ -12,6 +12,7 @@
 // the CPU reference.  They serve every configuration; the tuned batch kernel lives in
 // kernels_batch.cu.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include "lwsb_common.h"
 #include "kernels.h"
 #include "exact.cuh"

@@ -1,0 +1,294 @@
+// kernels_online.cu -- online_lws (TF-RTISI-LA, lwslib.cpp:1424-1492) with the working set in shared memory
+// and the update rule resolved at compile time.
+//
+// The whole schedule is one chain of row updates (lwsb_common.h: lwsb_online_decode); row update j runs S bins
+// behind row update j-1, S = the smallest multiple of Q that is >= L+1, so that at any step every thread of the
+// CTA is on a bin of the SAME residue p = bin mod Q: the per-residue weights then come out of the kernel
+// parameter bank with compile-time indices and one `switch (p)` selects the code for the step.  The ~Nreal/S
+// row updates in flight touch only the extended rows [m_lo - LA, m_hi + 2(Q-1)]; a ring of R rows (R a power
+// of two, sized on the host from the exact maximum of the schedule) keeps them in shared memory, rows are
+// copied in when the front of the chain first needs them and written back when the tail has passed.
+// One CTA per utterance.  Arithmetic: the reference's, operation for operation (exact.cuh).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <type_traits>
+#include "exact.cuh"
+#include "kernels.h"
+#include "lwsb_common.h"
+
+namespace lwsb {
+
+namespace {
+
+constexpr int OL = 5; // stencil reach this kernel is specialised for
+
+template <int Q>
+struct OnlineW { // the three weight sets (W, W_ai, W_af) in the reference layout, in the kernel parameter bank
+    double wr[3][Q][Q][OL + 1];
+    double wi[3][Q][Q][OL + 1];
+    unsigned flag[3][Q][Q]; // bit k: |W[p][r][k]| > 1e-12
+};
+
+struct OnlineRingCell {
+    const double2 *ring;
+    int rmask, pitch, row, col;
+    __device__ __forceinline__ double2 operator()(int dr, int dk) const
+    {
+        return ring[(size_t)((row + dr) & rmask) * pitch + col + dk];
+    }
+};
+
+// Asym_UpdatePhase{Q2,Q4,anyQ} for one bin of residue P (lwslib.cpp:776-1273): frame pairs r < rframe on both
+// sides, r >= rframe on the left only, centre-frame terms when cframe; weight set `ws` chosen at run time.
+//
+// The lanes of a warp are on different row updates (init / look-ahead / newest frame: different rframe, cframe
+// and weight set), so the rule is written WITHOUT data-dependent branches:
+//   * a "left only" term is the two-sided term with zeros in place of the frame m+r values -- bit-identical:
+//     ar*(br+0) - ai*(bi-0) = ar*br - ai*bi (lwslib.cpp:500-501), and for the folded forms b = e1 -+ 0,
+//     c = 0 -+ e4 reproduces c = -+E[m-r][n+k] (lwslib.cpp:994-997) exactly;
+//   * a term whose |W| <= 1e-12 flag is clear, or a centre term without cframe, is computed and dropped by a
+//     select (the reference skips it; adding nothing is the same).
+template <int Q, int P, int FOLD>
+__device__ __forceinline__ void online_weighted_sum(const OnlineRingCell &E, const OnlineW<Q> &w, int ws, int rframe, int cframe,
+                                                    double &tr, double &ti)
+{
+    constexpr int PN = (Q - P) % Q;
+    tr = 0.0; ti = 0.0;
+    const double2 zero = make_double2(0.0, 0.0);
+    auto add_if = [&](bool f, double ar, double ai, double br, double bi, double cr, double ci) {
+        const double nr = __dadd_rn(tr, __dsub_rn(__dmul_rn(ar, __dadd_rn(br, cr)), __dmul_rn(ai, __dsub_rn(bi, ci))));
+        const double ni = __dadd_rn(ti, __dadd_rn(__dmul_rn(ar, __dadd_rn(bi, ci)), __dmul_rn(ai, __dsub_rn(br, cr))));
+        tr = f ? nr : tr; ti = f ? ni : ti;
+    };
+    {
+        const unsigned f0 = cframe ? w.flag[ws][P][0] : 0u;
+#pragma unroll
+        for (int k = 1; k <= OL; ++k) {
+            const double2 b = E(0, -k), c = E(0, +k);
+            add_if((f0 >> k) & 1u, w.wr[ws][P][0][k], w.wi[ws][P][0][k], b.x, b.y, c.x, c.y);
+        }
+    }
+    auto pair = [&](auto rc, auto minusc) {
+        constexpr int r = decltype(rc)::value;
+        constexpr bool minus = decltype(minusc)::value;
+        const unsigned f = w.flag[ws][P][r], fn = w.flag[ws][PN][r];
+        const bool both = r < rframe;
+        {
+            const double2 b = E(-r, 0), c0 = E(+r, 0);
+            const double2 c = both ? c0 : zero;
+            add_if(f & 1u, w.wr[ws][P][r][0], w.wi[ws][P][r][0], b.x, b.y, c.x, c.y);
+        }
+#pragma unroll
+        for (int k = 1; k <= OL; ++k) {
+            const double2 e1 = E(-r, -k), e4 = E(-r, +k), e2l = E(+r, +k), e3l = E(+r, -k);
+            const double2 e2 = both ? e2l : zero, e3 = both ? e3l : zero;
+            if (FOLD == LWSB_FOLD_ANY) {
+                add_if((f >> k) & 1u, w.wr[ws][P][r][k], w.wi[ws][P][r][k], e1.x, e1.y, e3.x, e3.y);
+                add_if((fn >> k) & 1u, w.wr[ws][PN][r][k], w.wi[ws][PN][r][k], e2.x, e2.y, e4.x, e4.y);
+            } else {
+                double br, bi, cr, ci;
+                if (minus) {
+                    br = __dsub_rn(e1.x, e2.x); bi = __dsub_rn(e1.y, e2.y);
+                    cr = __dsub_rn(e3.x, e4.x); ci = __dsub_rn(e3.y, e4.y);
+                } else {
+                    br = __dadd_rn(e1.x, e2.x); bi = __dadd_rn(e1.y, e2.y);
+                    cr = __dadd_rn(e3.x, e4.x); ci = __dadd_rn(e3.y, e4.y);
+                }
+                add_if((f >> k) & 1u, w.wr[ws][P][r][k], w.wi[ws][P][r][k], br, bi, cr, ci);
+            }
+        }
+    };
+    using T_ = std::true_type;
+    using F_ = std::false_type;
+    if constexpr (FOLD == LWSB_FOLD_Q4 && (P & 1)) { // odd bins: r = 1, 3 sign-flipped, then r = 2 (lwslib.cpp:953-1052)
+        pair(std::integral_constant<int, 1>{}, T_{});
+        pair(std::integral_constant<int, 3>{}, T_{});
+        pair(std::integral_constant<int, 2>{}, F_{});
+    } else {
+        if constexpr (Q > 1) pair(std::integral_constant<int, 1>{}, F_{});
+        if constexpr (Q > 2) pair(std::integral_constant<int, 2>{}, F_{});
+        if constexpr (Q > 3) pair(std::integral_constant<int, 3>{}, F_{});
+        if constexpr (Q > 4) pair(std::integral_constant<int, 4>{}, F_{});
+        if constexpr (Q > 5) pair(std::integral_constant<int, 5>{}, F_{});
+        if constexpr (Q > 6) pair(std::integral_constant<int, 6>{}, F_{});
+        if constexpr (Q > 7) pair(std::integral_constant<int, 7>{}, F_{});
+    }
+}
+
+template <int Q, int FOLD, int P>
+__device__ __forceinline__ void online_sum_for_residue(int p, const OnlineRingCell &E, const OnlineW<Q> &w, int ws, int rframe,
+                                                       int cframe, double &tr, double &ti)
+{
+    if constexpr (P < Q) {
+        if (p == P) online_weighted_sum<Q, P, FOLD>(E, w, ws, rframe, cframe, tr, ti);
+        else online_sum_for_residue<Q, FOLD, P + 1>(p, E, w, ws, rframe, cframe, tr, ti);
+    }
+}
+
+template <int Q, int FOLD>
+__global__ void __launch_bounds__(256)
+k_online_ring(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *thresholds, int iters, int LA, int R, int pitch,
+              int S, unsigned *status)
+{
+    extern __shared__ __align__(16) unsigned char online_smem[];
+    double2 *ring = reinterpret_cast<double2 *>(online_smem);
+    // the weight sets are indexed per lane (each lane its own row update): shared memory serves divergent
+    // addresses at full rate, the constant bank would replay them
+    __shared__ OnlineW<Q> wsm;
+    for (int i = threadIdx.x; i < (int)(sizeof(OnlineW<Q>) / 4); i += blockDim.x)
+        reinterpret_cast<unsigned *>(&wsm)[i] = reinterpret_cast<const unsigned *>(&w)[i];
+    __syncthreads();
+    const int u = blockIdx.x;
+    const int T = v.T[u], Nreal = v.Nreal, P = v.P;
+    constexpr int L = OL;
+    const int Np = Nreal + 2 * L, Tp = T + 2 * (Q - 1), rmask = R - 1;
+    double2 *E0 = v.E + v.rowbase[u] * (long long)P + (v.c0 - L); // extended (row 0, column 0)
+    const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
+    const double mean = v.mean_amp[u];
+    const long long n = lwsb_online_chain_len(T, iters, LA);
+    const long long tmax = (long long)S * (n - 1) + (Nreal - 1);
+    const int nt = blockDim.x;
+    int lo = 0, hi = -1; // extended rows [lo, hi] are resident
+    long long jc = -1;
+    LwsbOnlineTask task;
+    double thr = 0.0, a_next = 0.0;
+    for (long long t = 0; t <= tmax; ++t) {
+        if (t % S == 0) { // the front of the chain moves to a new row update: residency check (uniform across the CTA)
+            const long long jhi = min(t / S, n - 1);
+            long long jlo = t < Nreal ? 0 : (t - (Nreal - 1) + S - 1) / S;
+            if (jlo > n - 1) jlo = n - 1;
+            const int need_hi = min(Tp - 1, lwsb_online_frame(iters, LA, jhi) + 2 * (Q - 1));
+            const int need_lo = max(0, lwsb_online_frame(iters, LA, jlo) - LA);
+            if (need_hi > hi) {
+                if (need_hi - need_lo + 1 > R && threadIdx.x == 0) atomicCAS(status, 0u, 0xE1000000u | (unsigned)u);
+                for (int e = lo; e < need_lo; ++e) // rows the chain has left: back to global memory
+                    if (e >= Q - 1 && e < T + Q - 1)
+                        for (int x = threadIdx.x; x < Np; x += nt) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+                lo = need_lo;
+                __syncthreads();
+                for (int e = hi + 1; e <= need_hi; ++e) // rows the chain is about to reach
+                    for (int x = threadIdx.x; x < Np; x += nt) ring[(size_t)(e & rmask) * pitch + x] = E0[(long long)e * P + x];
+                hi = need_hi;
+                __syncthreads();
+            }
+        }
+        const long long jhi = t / S;
+        const long long d = (jhi - threadIdx.x) % nt;
+        const long long j = jhi - (d < 0 ? d + nt : d);
+        if (j >= 0 && j < n) {
+            const int c = (int)(t - (long long)S * j);
+            if (c < Nreal) {
+                double a;
+                if (j != jc) {
+                    jc = j;
+                    task = lwsb_online_decode(T, iters, LA, Q, j);
+                    thr = task.thr < 0 ? 0.0 : __dmul_rn(thresholds[task.thr], mean); // lws.pyx:361, lwslib.cpp:1467
+                    a = A0[(long long)task.row * P + L + c];
+                } else a = a_next;
+                if (c + 1 < Nreal) a_next = __ldg(A0 + (long long)task.row * P + L + c + 1); // amplitude of the next step
+                if (a > thr) { // lwslib.cpp:295-296
+                    double2 *Rrow = ring + (size_t)(task.row & rmask) * pitch;
+                    const OnlineRingCell cell{ring, rmask, pitch, task.row, L + c};
+                    double tr = 0.0, ti = 0.0;
+                    online_sum_for_residue<Q, FOLD, 0>(c % Q, cell, wsm, task.which, task.rframe, task.cframe, tr, ti);
+                    double2 val;
+                    if (x_project(tr, ti, a, val)) {
+                        Rrow[L + c] = val;
+                        if (c >= 1 && c <= L) Rrow[L - c] = make_double2(val.x, -val.y);
+                        else if (c >= Nreal - 1 - L && c <= Nreal - 2) Rrow[L + 2 * (Nreal - 1) - c] = make_double2(val.x, -val.y);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = lo; e <= hi; ++e)
+        if (e >= Q - 1 && e < T + Q - 1)
+            for (int x = threadIdx.x; x < Np; x += nt) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+}
+
+// Largest number of extended rows resident at once: rows are loaded when the front of the chain first needs
+// them (at steps t = k*S) and rows behind the tail are dropped at the same moment -- same formulas as the kernel.
+int online_max_span(int T, int Nreal, int S, int Q, int iters, int LA)
+{
+    const long long n = lwsb_online_chain_len(T, iters, LA);
+    const int Tp = T + 2 * (Q - 1);
+    int span = 0;
+    for (long long k = 0; k < n; ++k) {
+        const long long t = k * S;
+        long long jl = t < Nreal ? 0 : (t - (Nreal - 1) + S - 1) / S;
+        if (jl > n - 1) jl = n - 1;
+        const int hi = std::min(Tp - 1, lwsb_online_frame(iters, LA, k) + 2 * (Q - 1));
+        const int lo = std::max(0, lwsb_online_frame(iters, LA, jl) - LA);
+        span = std::max(span, hi - lo + 1);
+    }
+    return span;
+}
+
+template <int Q, int FOLD>
+cudaError_t launch_t(const LwsbView &v, const OnlineW<Q> &w, const double *thr, int iters, int LA, int R, int pitch, int S, int nt,
+                     size_t bytes, unsigned *status, cudaStream_t s)
+{
+    auto kern = k_online_ring<Q, FOLD>;
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<v.B, nt, bytes, s>>>(v, w, thr, iters, LA, R, pitch, S, status);
+    return cudaGetLastError();
+}
+
+template <int Q>
+cudaError_t launch_q(const LwsbView &v, const double *const *wr, const double *const *wi, int fold, const double *thr, int iters,
+                     int LA, int R, int pitch, int S, int nt, size_t bytes, unsigned *status, cudaStream_t s)
+{
+    OnlineW<Q> w;
+    for (int ws = 0; ws < 3; ++ws)
+        for (int p = 0; p < Q; ++p)
+            for (int r = 0; r < Q; ++r) {
+                unsigned f = 0;
+                for (int k = 0; k <= OL; ++k) {
+                    const size_t i = ((size_t)p * Q + r) * (OL + 1) + k;
+                    w.wr[ws][p][r][k] = wr[ws][i]; w.wi[ws][p][r][k] = wi[ws][i];
+                    if (std::hypot(wr[ws][i], wi[ws][i]) > 1.0e-12) f |= 1u << k; // lws.pyx:347-352
+                }
+                w.flag[ws][p][r] = f;
+            }
+    if (fold == LWSB_FOLD_ANY) return launch_t<Q, LWSB_FOLD_ANY>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, s);
+    if constexpr (Q == 4) { if (fold == LWSB_FOLD_Q4) return launch_t<4, LWSB_FOLD_Q4>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, s); }
+    if constexpr (Q == 2) { if (fold == LWSB_FOLD_Q2) return launch_t<2, LWSB_FOLD_Q2>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, s); }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace
+
+// returns false when this kernel does not serve the shape (the global-memory kernel takes over)
+bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const double *const *wi_host, int fold,
+                        const double *thr, int iters, int LA, const int *T_host, size_t smem_limit, unsigned *status,
+                        cudaStream_t s, cudaError_t *err)
+{
+    *err = cudaSuccess;
+    const int Q = v.Q;
+    if (v.L != OL || !(Q == 2 || Q == 4 || Q == 8)) return false;
+    const int S = (OL + 1 + Q - 1) / Q * Q; // smallest multiple of Q >= L + 1: every thread of a step on the same residue
+    int span = 0, lastT = -1;
+    for (int b = 0; b < v.B; ++b) // exact span for every distinct length of the batch
+        if (T_host[b] != lastT) { lastT = T_host[b]; span = std::max(span, online_max_span(lastT, v.Nreal, S, Q, iters, LA)); }
+    int R = 8;
+    while (R < span) R *= 2;
+    int pitch = v.Nreal + 2 * OL;
+    if ((pitch & 1) == 0) ++pitch;
+    const size_t bytes = (size_t)R * pitch * sizeof(double2);
+    if (bytes + (size_t)Q * Q * 3 * ((OL + 1) * 16 + 4) + 1024 > smem_limit) return false; // ring + the weight sets
+    int nt = (v.Nreal + S - 1) / S + 1;
+    nt = (nt + 31) / 32 * 32;
+    if (nt > 256) return false;
+    switch (Q) {
+    case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, s); break;
+    case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, s); break;
+    case 8: *err = launch_q<8>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, s); break;
+    }
+    return true;
+}
+
+} // namespace lwsb

@@ -50,21 +50,21 @@ LWSB_HD long long lwsb_online_frame_base(int m, int it, int LA)
 
 LWSB_HD long long lwsb_online_chain_len(int T, int it, int LA) { return lwsb_online_frame_base(T, it, LA); }
 
+// frame whose block of row updates contains chain position j
+LWSB_HD int lwsb_online_frame(int it, int LA, long long j)
+{
+    if (LA <= 0) return (int)(j / (1 + it));
+    const long long bLA = lwsb_online_frame_base(LA, it, LA);
+    if (j >= bLA) return LA + (int)((j - bLA) / (1 + (long long)it * (LA + 1)));
+    int m = 0;
+    while (lwsb_online_frame_base(m + 1, it, LA) <= j) ++m;
+    return m;
+}
+
 LWSB_HD LwsbOnlineTask lwsb_online_decode(int T, int it, int LA, int Q, long long j)
 {
     (void)T;
-    int m;
-    if (LA <= 0) {
-        m = (int)(j / (1 + it));
-    } else {
-        long long bLA = lwsb_online_frame_base(LA, it, LA);
-        if (j >= bLA) {
-            m = LA + (int)((j - bLA) / (1 + (long long)it * (LA + 1)));
-        } else {
-            m = 0;
-            while (lwsb_online_frame_base(m + 1, it, LA) <= j) ++m;
-        }
-    }
+    const int m = lwsb_online_frame(it, LA, j);
     const int nf = (LA > 0) ? (m < LA ? m : LA) : 0;
     long long rem = j - lwsb_online_frame_base(m, it, LA);
     LwsbOnlineTask t;
