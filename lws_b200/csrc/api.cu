@@ -57,8 +57,10 @@ struct lwsb_ctx {
     long long total_rows = 0, total_bins = 0;
     std::vector<int> T;
     std::vector<long long> rowbase, binbase;
-    DevBuf E, A, row_max, leaf_tab, leaf_sum, mean_amp, max_amp, dT, drowbase, stage, dptr, dthr, flags;
+    DevBuf E, A, row_max, leaf_tab, tab_of, leaf_sum, mean_amp, max_amp, dT, drowbase, stage, dptr, dthr, flags;
     long long leaf_stride = 0;
+    std::vector<int> stat_tabs;                         // host copy of the summation trees, concatenated
+    std::map<long long, std::pair<int, int>> stat_index; // array length -> (first leaf, leaf count)
     DevBuf fx, fS, fwin, fframes;          // stft / istft staging
     DevBuf status;                         // watchdog word of the strip kernel
     int last_kernel = 0;                   // 0 generic, 1 strips (introspection)
@@ -86,7 +88,7 @@ struct lwsb_ctx {
     }
     StatScratch scratch() const
     {
-        return StatScratch{row_max.as<double>(), leaf_tab.as<int>(), leaf_sum.as<double>(), leaf_stride};
+        return StatScratch{row_max.as<double>(), leaf_tab.as<const int>(), tab_of.as<const int2>(), leaf_sum.as<double>(), leaf_stride};
     }
     LwsbW devw(int which) const
     {
@@ -194,7 +196,7 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
     CHECK_CTX(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->E, &c->A, &c->row_max, &c->leaf_tab, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
+    for (DevBuf *b : {&c->E, &c->A, &c->row_max, &c->leaf_tab, &c->tab_of, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
                       &c->drowbase, &c->stage, &c->dptr, &c->dthr, &c->flags, &c->fx, &c->fS, &c->fwin, &c->fframes, &c->status})
         b->release();
     for (auto &kv : c->twiddles) kv.second.release();
@@ -310,9 +312,25 @@ extern "C" int lwsb_load(lwsb_ctx *c, const void *const *S_in, const int *T, int
     CU(c, c->E.reserve((size_t)rows * P * sizeof(double2)));
     CU(c, c->A.reserve((size_t)rows * P * sizeof(double)));
     CU(c, c->row_max.reserve((size_t)rows * sizeof(double)));
+    // numpy's summation tree per distinct array length (cached for the life of the context)
     long long stride = 0;
-    for (int b = 0; b < B; ++b) stride = std::max(stride, stat_leaves_bound((long long)T[b] * Nreal));
-    CU(c, c->leaf_tab.reserve((size_t)B * stride * 3 * sizeof(int)));
+    std::vector<int2> tab_of(B);
+    for (int b = 0; b < B; ++b) {
+        const long long n = (long long)T[b] * Nreal;
+        auto it = c->stat_index.find(n);
+        if (it == c->stat_index.end()) {
+            const int first = (int)(c->stat_tabs.size() / 3);
+            stat_tree(n, c->stat_tabs);
+            it = c->stat_index.emplace(n, std::make_pair(first, (int)(c->stat_tabs.size() / 3) - first)).first;
+        }
+        tab_of[b] = make_int2(it->second.first, it->second.second);
+        stride = std::max(stride, (long long)it->second.second);
+    }
+    CU(c, c->leaf_tab.reserve(std::max<size_t>(c->stat_tabs.size(), 3) * sizeof(int)));
+    // (re)sent on every load: a few tens of KB, and reserve() may have moved the buffer
+    CU(c, cudaMemcpyAsync(c->leaf_tab.p, c->stat_tabs.data(), c->stat_tabs.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(c, c->tab_of.reserve(B * sizeof(int2)));
+    CU(c, cudaMemcpyAsync(c->tab_of.p, tab_of.data(), B * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
     CU(c, c->leaf_sum.reserve((size_t)B * stride * sizeof(double)));
     c->leaf_stride = stride;
     CU(c, c->mean_amp.reserve(B * sizeof(double)));

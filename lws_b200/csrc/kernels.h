@@ -1,6 +1,7 @@
 // kernels.h -- launch wrappers implemented in the .cu files (host-callable).
 #pragma once
 #include <cuda_runtime.h>
+#include <vector>
 #include "lwsb_common.h"
 #include "exact.cuh"
 
@@ -9,11 +10,12 @@ namespace lwsb {
 // kernels_generic.cu
 struct StatScratch {     // work space of the numpy-ordered mean (k_stats)
     double *row_max;     // [total rows]
-    int *leaf_tab;       // [B][stride][3]
+    const int *leaf_tab; // summation trees (offset, length, additions-after) of the array lengths in the batch
+    const int2 *tab_of;  // [B] (first leaf, leaf count) of utterance b's tree in leaf_tab
     double *leaf_sum;    // [B][stride]
     long long stride;    // leaves reserved per utterance
 };
-inline long long stat_leaves_bound(long long n) { return n / 32 + 8; } // leaves hold > 32 elements once n > 128
+void stat_tree(long long n, std::vector<int> &tab); // host: numpy's pairwise-summation tree for n elements
 
 void launch_extend(const LwsbView &v, int kind, const void *const *src, const StatScratch &sc, double *mean_amp,
                    double *max_amp, int maxTp, cudaStream_t s);

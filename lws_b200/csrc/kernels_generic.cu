@@ -13,6 +13,7 @@
 // kernels_batch.cu.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <vector>
 #include "lwsb_common.h"
 #include "kernels.h"
 #include "exact.cuh"
@@ -81,67 +82,46 @@ __global__ void k_extend(LwsbView v, const void *const *src, double *row_max)
 // elements summed with 8 interleaved accumulators, halves split at a multiple of 8) divided by
 // the element count.  The thresholds are multiples of this number and the comparison
 // `absspec > threshold` (lwslib.cpp:296) decides which bins move, so the sum is reproduced
-// in the same order: thread 0 walks the recursion and emits the leaf blocks plus, per leaf, how
-// many pending partial sums to combine after it; all threads sum leaves; thread 0 combines.
-__device__ __forceinline__ double amp_at(const LwsbView &v, long long row0, long long i)
-{
-    const long long r = i / v.Nreal;
-    const int c = (int)(i - r * v.Nreal);
-    return v.A[(row0 + r) * v.P + v.c0 + c];
-}
-
-__global__ void __launch_bounds__(256)
-k_stats(LwsbView v, const double *row_max, double *mean_amp, double *max_amp, int *leaf_tab, double *leaf_sum,
+// in the same order: the host walks the recursion once per array length (stat_tree) and emits the
+// leaf blocks plus, per leaf, how many pending partial sums to combine after it; all threads sum
+// leaves; thread 0 combines.
+__global__ void __launch_bounds__(1024)
+k_stats(LwsbView v, const double *row_max, double *mean_amp, double *max_amp, const int *leaf_tab, const int2 *tab_of, double *leaf_sum,
         long long scratch_stride)
 {
     const int u = blockIdx.x;
     const int T = v.T[u];
     const long long row0 = v.rowbase[u] + (v.Q - 1);
     const long long n = (long long)T * v.Nreal;
-    int *tab = leaf_tab + (size_t)u * scratch_stride * 3; // (offset, length, adds-after) per leaf
+    const int *tab = leaf_tab + 3 * (size_t)tab_of[u].x; // (offset, length, adds-after) per leaf: built on the host (stat_tree)
+    const int n_leaves = tab_of[u].y;
     double *ls = leaf_sum + (size_t)u * scratch_stride;
-    __shared__ int n_leaves;
     __shared__ double sh_m[32];
-    if (threadIdx.x == 0) {
-        // post-order walk of pairwise(a, n) = n <= 128 ? leaf : pairwise(a, n2) + pairwise(a + n2, n - n2)
-        long long off[64], len[64];
-        int state[64], sp = 0, nl = 0;
-        off[0] = 0; len[0] = n; state[0] = 0; sp = 1;
-        while (sp > 0) {
-            const int top = sp - 1;
-            if (len[top] <= 128) {
-                tab[3 * nl] = (int)off[top]; tab[3 * nl + 1] = (int)len[top]; tab[3 * nl + 2] = 0;
-                ++nl; --sp;
-            } else if (state[top] == 0) {
-                long long n2 = len[top] / 2; n2 -= n2 % 8;
-                state[top] = 1;
-                // right child is pushed first so that the left one is processed first
-                off[sp] = off[top] + n2; len[sp] = len[top] - n2; state[sp] = 0; ++sp;
-                off[sp] = off[top]; len[sp] = n2; state[sp] = 0; ++sp;
-            } else {
-                tab[3 * (nl - 1) + 2] += 1; // both children done: one addition after the last leaf emitted
-                --sp;
-            }
-        }
-        n_leaves = nl;
-    }
-    __syncthreads();
     for (int l = threadIdx.x; l < n_leaves; l += blockDim.x) {
         const long long lo = tab[3 * l];
         const int m = tab[3 * l + 1];
+        // walk the leaf with a running (frame, bin) position instead of dividing per element
+        long long fr = lo / v.Nreal;
+        int bin = (int)(lo - fr * v.Nreal);
+        const double *Arow = v.A + (row0 + fr) * v.P + v.c0;
+        auto next = [&]() {
+            const double a = Arow[bin];
+            if (++bin == v.Nreal) { bin = 0; Arow += v.P; }
+            return a;
+        };
         double res;
         if (m < 8) {
             res = 0.0;
-            for (int i = 0; i < m; ++i) res = __dadd_rn(res, amp_at(v, row0, lo + i));
+            for (int i = 0; i < m; ++i) res = __dadd_rn(res, next());
         } else {
             double r[8];
-            for (int j = 0; j < 8; ++j) r[j] = amp_at(v, row0, lo + j);
+            for (int j = 0; j < 8; ++j) r[j] = next();
             int i = 8;
             for (; i < m - (m % 8); i += 8)
-                for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], amp_at(v, row0, lo + i + j));
+                for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], next());
             res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
                             __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-            for (; i < m; ++i) res = __dadd_rn(res, amp_at(v, row0, lo + i));
+            for (; i < m; ++i) res = __dadd_rn(res, next());
         }
         ls[l] = res;
     }
@@ -407,6 +387,34 @@ k_nofuture_q4(LwsbView v, const double *wr, const double *wi, const int *wf, con
 }
 
 // ------------------------------------------------------------------------------------------
+// post-order walk of numpy's pairwise(a, n) = n <= 128 ? leaf : pairwise(a, n2) + pairwise(a + n2, n - n2),
+// n2 = (n/2) rounded down to a multiple of 8: appends (offset, length, additions after this leaf) triples
+void stat_tree(long long n, std::vector<int> &tab)
+{
+    struct Node { long long off, len; int state; };
+    std::vector<Node> st;
+    st.push_back(Node{0, n, 0});
+    const size_t first = tab.size();
+    while (!st.empty()) {
+        Node &top = st.back();
+        if (top.len <= 128) {
+            tab.push_back((int)top.off); tab.push_back((int)top.len); tab.push_back(0);
+            st.pop_back();
+        } else if (top.state == 0) {
+            long long n2 = top.len / 2; n2 -= n2 % 8;
+            top.state = 1;
+            const Node right{top.off + n2, top.len - n2, 0}, left{top.off, n2, 0};
+            st.push_back(right); // the left half is processed first
+            st.push_back(left);
+        } else {
+            tab[tab.size() - 1] += 1; // both halves done: one addition after the last leaf emitted
+            st.pop_back();
+        }
+    }
+    (void)first;
+}
+
+// ------------------------------------------------------------------------------------------
 // launch wrappers
 void launch_extend(const LwsbView &v, int kind, const void *const *src, const StatScratch &sc, double *mean_amp,
                    double *max_amp, int maxTp, cudaStream_t s)
@@ -414,7 +422,7 @@ void launch_extend(const LwsbView &v, int kind, const void *const *src, const St
     dim3 grid(maxTp, v.B);
     if (kind == 0) k_extend<0><<<grid, 256, 0, s>>>(v, src, sc.row_max);
     else k_extend<1><<<grid, 256, 0, s>>>(v, src, sc.row_max);
-    k_stats<<<v.B, 256, 0, s>>>(v, sc.row_max, mean_amp, max_amp, sc.leaf_tab, sc.leaf_sum, sc.stride);
+    k_stats<<<v.B, 1024, 0, s>>>(v, sc.row_max, mean_amp, max_amp, sc.leaf_tab, sc.tab_of, sc.leaf_sum, sc.stride);
 }
 
 void launch_refresh_ghosts(const LwsbView &v, cudaStream_t s)
@@ -430,7 +438,7 @@ void launch_reextend(const LwsbView &v, const StatScratch &sc, double *mean_amp,
     dim3 grid(maxTp, v.B);
     k_reamp<<<grid, 256, 0, s>>>(v, sc.row_max);
     launch_refresh_ghosts(v, s);
-    k_stats<<<v.B, 256, 0, s>>>(v, sc.row_max, mean_amp, max_amp, sc.leaf_tab, sc.leaf_sum, sc.stride);
+    k_stats<<<v.B, 1024, 0, s>>>(v, sc.row_max, mean_amp, max_amp, sc.leaf_tab, sc.tab_of, sc.leaf_sum, sc.stride);
 }
 
 void launch_crop(const LwsbView &v, void *const *dst, int maxT, cudaStream_t s)
