@@ -135,9 +135,15 @@ int lwsb_last_batch_plan(const lwsb_ctx *ctx, int *out9);
  * size (1, 2, 4, 8) and sweeps in flight per pass.  Also settable through the environment variables
  * LWSB_STRIP_SMEM / LWSB_STRIP_CLUSTER / LWSB_STRIP_SWEEPS (and LWSB_STRIP_LAG, LWSB_STRIP_TM) read by lwsb_create().  Results do not depend on them. */
 int lwsb_set_tuning(lwsb_ctx *ctx, long long smem_limit, int cluster, int sweeps_per_pass);
-/* kernel variant knobs: frames between consecutive sweeps (0 = automatic, else >= Q) and the experimental
- * tensor-memory producer/consumer variant of the strip kernel (0 = off, the default; 1 = on) */
+/* kernel variant knobs: frames between consecutive sweeps (0 = automatic, else >= Q) and the variant of the strip
+ * kernel: 0 = automatic (two lanes per task -- "pair-split" -- where the folded Q = 2 / Q = 4 updates allow it),
+ * 1 = experimental tensor-memory producer/consumer warps, 2 = one thread per task, 10..15 = pair-split with
+ * register-window mode (0..2) + 3 * explicit software pipelining (modes other than the default one exist only in
+ * builds with -DLWSB_PAIR_EXPERIMENTS and otherwise select the default).  Results do not depend on it. */
 int lwsb_set_variant(lwsb_ctx *ctx, int sweep_lag, int tensor_memory);
+/* self-check of the branch-free sqrt / division of the pair-split kernels against the CUDA library functions on
+ * n pseudo-random inputs: out4 = {sqrt samples in the fast range, of which differing, division samples, differing} */
+int lwsb_debug_fast_math(lwsb_ctx *ctx, long long n, unsigned long long seed, unsigned long long *out4);
 /* cycle accounting of cluster 0 in the last strip-kernel launch, summed over its CTAs: control lane {publish,
  * poll neighbours, TMA housekeeping}, compute warps {work, wait for the strip, wait for the neighbours, warps} */
 int lwsb_last_batch_cycles(lwsb_ctx *ctx, unsigned long long *out13); /* + 6 consumer-phase counters (TM kernels) */

@@ -55,6 +55,7 @@ SIGNATURES = {
     "lwsb_set_tuning": (_ci, [_vp, _ll, _ci, _ci]),
     "lwsb_set_variant": (_ci, [_vp, _ci, _ci]),
     "lwsb_last_batch_cycles": (_ci, [_vp, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "lwsb_debug_fast_math": (_ci, [_vp, _ll, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]),
     "lwsb_debug_online_chain_length": (_ll, [_ci, _ci, _ci]),
     "lwsb_debug_online_task": (_ci, [_ci, _ci, _ci, _ci, _ll, _ip, _ip, _ip, _ip, _ip]),
 }
@@ -261,6 +262,12 @@ class Context(object):
 
     def set_variant(self, sweep_lag=0, tensor_memory=0):
         self._c(lib().lwsb_set_variant(self._h, int(sweep_lag), int(tensor_memory)))
+
+    def debug_fast_math(self, n, seed=1):
+        """(sqrt samples checked, differing, division samples checked, differing) of the kernels' branch-free sqrt / division."""
+        out = (ctypes.c_ulonglong * 4)()
+        self._c(lib().lwsb_debug_fast_math(self._h, int(n), int(seed), out))
+        return tuple(int(x) for x in out)
 
     def last_batch_cycles(self):
         out = (ctypes.c_ulonglong * 13)()

@@ -28,17 +28,39 @@ def _newest_source():
 
 
 def build(force=False, verbose=False):
+    """One nvcc process per translation unit (in parallel), then a link step.  LWSB_NVCC_EXTRA adds flags
+    (e.g. -DLWSB_PAIR_EXPERIMENTS for the kernel-variant experiments of tools/gpu_pair.py)."""
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout)
-    if res.returncode != 0:
+    extra = os.environ.get("LWSB_NVCC_EXTRA", "").split()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("--shared",)]
+    procs = []
+    for s in srcs:
+        obj = os.path.join(objdir, s[:-3] + ".o")
+        cmd = [nvcc] + compile_flags + extra + ["-c", "-o", obj, os.path.join(CSRC, s)]
+        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log, failed = [], False
+    for cmd, obj, pr in procs:
+        out = pr.communicate()[0]
+        log.append(" ".join(cmd) + "\n" + out)
+        failed = failed or pr.returncode != 0
+    if not failed:
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-Xcompiler", "-fPIC",
+               "-o", LIB] + [obj for _, obj, _ in procs]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log.append(" ".join(cmd) + "\n" + res.stdout)
+        failed = res.returncode != 0
+    text = "\n".join(log)
+    if verbose or failed:
+        sys.stderr.write(text)
+    if failed:
         raise RuntimeError("nvcc failed building liblws_b200.so")
     with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + res.stdout)
+        f.write(text)
     return LIB
 
 

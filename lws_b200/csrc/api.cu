@@ -428,7 +428,7 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
                         plan_strips(c->Nreal, c->Q, c->L, active, c->maxT, c->B,
                                     c->tune_smem > 0 ? std::min((size_t)c->tune_smem, c->prop.sharedMemPerBlockOptin)
                                                      : c->prop.sharedMemPerBlockOptin,
-                                    c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps, c->tune_lag, c->tune_tm) &&
+                                    c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps, c->tune_lag, c->tune_tm, fold) &&
                         c->P >= strips_min_pitch(c->Nreal, c->c0);
     if (strips) {
         CU(c, c->status.reserve(256));
@@ -736,10 +736,25 @@ extern "C" int lwsb_last_batch_cycles(lwsb_ctx *c, unsigned long long *out7)
     return 1;
 }
 
+extern "C" int lwsb_debug_fast_math(lwsb_ctx *c, long long n, unsigned long long seed, unsigned long long *out4)
+{
+    CHECK_CTX(c);
+    if (!out4 || n < 0) return fail(c, LWSB_ERR_ARG, "bad lwsb_debug_fast_math arguments");
+    if (int r = use_device(c)) return r;
+    CU(c, c->status.reserve(256));
+    CU(c, cudaMemsetAsync(c->status.p, 0, 256, c->stream));
+    CU(c, launch_debug_fast_math(n, seed, c->status.as<unsigned long long>(), c->stream));
+    c->launches += 1;
+    CU(c, cudaMemcpyAsync(out4, c->status.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->last_kernel = 0;
+    return LWSB_OK;
+}
+
 extern "C" int lwsb_set_tuning(lwsb_ctx *c, long long smem_limit, int cluster, int sweeps_per_pass)
 {
     CHECK_CTX(c);
-    if (smem_limit < 0 || cluster < 0 || cluster > 8 || (cluster & (cluster - 1)) || sweeps_per_pass < 0)
+    if (smem_limit < 0 || cluster < 0 || cluster > 8 || (cluster & (cluster - 1)))
         return fail(c, LWSB_ERR_ARG, "bad tuning values");
     c->tune_smem = smem_limit; c->tune_cluster = cluster; c->tune_sweeps = sweeps_per_pass;
     return LWSB_OK;
@@ -748,7 +763,8 @@ extern "C" int lwsb_set_tuning(lwsb_ctx *c, long long smem_limit, int cluster, i
 extern "C" int lwsb_set_variant(lwsb_ctx *c, int sweep_lag, int tensor_memory)
 {
     CHECK_CTX(c);
-    if (sweep_lag < 0 || tensor_memory < 0 || tensor_memory > 1) return fail(c, LWSB_ERR_ARG, "bad variant values");
+    if (sweep_lag < 0 || tensor_memory < 0 || (tensor_memory > LWSB_VARIANT_SCALAR && (tensor_memory < LWSB_VARIANT_PAIR || tensor_memory > LWSB_VARIANT_PAIR + 5)))
+        return fail(c, LWSB_ERR_ARG, "bad variant values");
     c->tune_lag = sweep_lag; c->tune_tm = tensor_memory;
     return LWSB_OK;
 }

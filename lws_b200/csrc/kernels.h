@@ -35,14 +35,16 @@ void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, in
 
 // kernels_batch.cu
 struct StripPlan {
-    int C, NBr, NBV, NS, G, R, pitch, nthreads, smem_bytes, QS, GFAST, TM;
+    int C, NBr, NBV, NS, G, R, pitch, nthreads, smem_bytes, QS, GFAST, TM; // TM: 0 one thread per task, LWSB_VARIANT_TM, LWSB_VARIANT_PAIR + window mode
 };
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
-                 int force_cluster = 0, int max_sweeps = 0, int force_lag = 0, int use_tm = 0);
+                 int force_cluster = 0, int max_sweeps = 0, int force_lag = 0, int variant = 0, int fold = 0);
 int strips_min_pitch(int Nreal, int c0);
 cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const double *wi_host, int fold,
                                 const double *thr, const double *max_amp, int iters, const StripPlan &pl,
                                 unsigned *status, cudaStream_t s);
+
+cudaError_t launch_debug_fast_math(long long n, unsigned long long seed, unsigned long long *out4, cudaStream_t s);
 
 // kernels_fft.cu
 cudaError_t launch_stft(const double *x, int B, int nsamples, const double *awin, int fsize, int hop, int N, int logN,

@@ -30,6 +30,7 @@
 #include <cstdint>
 #include <type_traits>
 #include "exact.cuh"
+#include "fast_math.cuh"
 #include "kernels.h"
 #include "lwsb_common.h"
 
@@ -43,6 +44,18 @@ constexpr int SL = 5;          // stencil reach in bins this kernel is specialis
 constexpr int SBK = 8;         // bins per block
 constexpr int SLEAD = 2;       // frames of TMA look-ahead
 constexpr unsigned SPIN_LIMIT = 1u << 22; // polls before a wait is declared dead (~0.5 s)
+#ifdef LWSB_PAIR_EXPERIMENTS
+constexpr int pair_thread_cap(int max_sweeps) { return max_sweeps < 0 ? 512 : 256; }
+#else
+constexpr int pair_thread_cap(int) { return 256; }
+#endif
+// planner cost model of the pair-split kernels (cycles per macro-step: fixed + per warp; weight of the bank-conflict factor)
+constexpr double PAIR_T0 = 8000.0, PAIR_T1 = 500.0, PAIR_TF = 0.3;
+constexpr int PAIR_THREADS_MAX = 512;  // pair-split kernels: 15 task warps (240 tasks) + the control warp at 128 registers
+constexpr int PAIR_THREADS_PLAN = 256; // what the planner uses: 7 task warps + the control warp keep 255 registers (measured fastest)
+#ifndef LWSB_PAIR_DEFAULT_MODE
+#define LWSB_PAIR_DEFAULT_MODE 1 // odd frame pairs (r = 1, 3) in register windows, no explicit pipelining
+#endif // pair-split kernels: 15 task warps (240 tasks) + the control warp at 128 registers
 
 template <int Q>
 struct StripW {                // one weight set, reference layout, in the kernel parameter bank
@@ -412,8 +425,22 @@ __device__ __forceinline__ void pipelined_block(RingCell<Q> &cell, const StripW<
                 }
             }
         bin_accumulate<Q, P, FOLD, PAT>(w, tv, tr, ti);
+        // |t| = sqrt(tr*tr + ti*ti), new value (t * a) / |t| (lwslib.cpp:355-360), branch free (fast_math.cuh): one
+        // reciprocal serves both divisions; the rare bin outside the fast ranges goes through the library functions
         double2 val;
-        const bool ok = x_project(tr, ti, amp[I], val) && ((active >> I) & 1u);
+        const double x = __dadd_rn(__dmul_rn(tr, tr), __dmul_rn(ti, ti));
+        const double nr = __dmul_rn(tr, amp[I]), ni = __dmul_rn(ti, amp[I]);
+        const bool act = (active >> I) & 1u;
+        bool sok, rok, dok1, dok2;
+        double mag = fm_sqrt(x, sok);
+        const double rcp = fm_rcp(mag, rok);
+        val.x = fm_div(nr, mag, rcp, dok1);
+        val.y = fm_div(ni, mag, rcp, dok2);
+        if (act && !(x == 0.0) && !(sok && rok && dok1 && dok2)) {
+            mag = __dsqrt_rn(x);
+            val.x = __ddiv_rn(nr, mag); val.y = __ddiv_rn(ni, mag);
+        }
+        const bool ok = act && x > 0.0;
         // (3) commit: own cell and its mirrored copy (lwslib.cpp:356-368)
         double2 *own = reinterpret_cast<double2 *>(bc.ring + bc.ownoff);
         const int n = bc.n0 + I;
@@ -454,6 +481,8 @@ __device__ __forceinline__ void strip_update_block_pipelined(RingCell<Q> &cell, 
             if ((committed >> i) & 1u) dst[i - (SBK - SL)] = newv[i];
     }
 }
+
+#include "strip_pair.cuh"
 
 // ---------------------------------------------------------------- tensor memory as a term-value scratch pad (TM kernels)
 // The register file cannot hold the 59 neighbour values of a bin for several bins at once, and shared memory is
@@ -634,11 +663,14 @@ __device__ __forceinline__ void tm_consume_bins(const StripW<Q> &w, const BlockC
 
 // ---------------------------------------------------------------- the kernel
 // TM = true: 8 warps, 0..3 consume and 4..7 produce (through tensor memory); needs the default mask
-template <int Q, int FOLD, int PAT, bool TM>
-__global__ void __maxnreg__(255)
+// PAIR > 0: two lanes per task (strip_pair.cuh); PAIR - 1 = window mode (0..2) + 3 * explicit pipelining (0/1); NREG: register cap
+template <int Q, int FOLD, int PAT, bool TM, int PAIR, int NREG>
+__global__ void __maxnreg__(NREG)
 k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ StripW<Q> w)
 {
     static_assert(!TM || (PAT == 1 && FOLD != LWSB_FOLD_ANY && Q <= 4), "the TMEM layout is laid out for the folded default-mask terms");
+    static_assert(!(TM && PAIR), "one variant at a time");
+    static_assert(!PAIR || Q <= 4, "the pair-split update is unrolled for Q <= 4");
     cg::cluster_group cluster = cg::this_cluster();
     const int C = prm.C;
     const int c = (int)cluster.block_rank();
@@ -679,7 +711,8 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
     // per-thread slot: frame residue j, sweep slot g
     // thread order: sweep slot fastest (lanes of a quarter-warp sit QS rows apart: conflict free for odd QS) or
     // frame slot fastest (lanes on consecutive frames); the planner picks the one with fewer bank conflicts
-    const int tix = TM ? (tid & 127) : tid;            // task index: producer lane l of warp w+4 serves consumer lane l of warp w
+    // task index: TM: producer lane l of warp w+4 serves consumer lane l of warp w; PAIR: lanes 2p, 2p+1 share task p
+    const int tix = TM ? (tid & 127) : (PAIR ? (tid >> 1) : tid);
     const bool is_producer = TM && tid >= 128 && !is_ctrl;
     const int j = prm.GFAST ? tix / G : tix % NS, g = prm.GFAST ? tix % G : tix / NS;
     const bool has_slot = !is_ctrl && j < NS && g < G;
@@ -923,6 +956,78 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                         else { tm_work += k1 - k0; tm_waitA += k2 - k1; tm_waitB += k3 - k2; }
                     }
                     if (ctl) fix_parity();
+                } else if constexpr (PAIR != 0) {
+                    // ---- two lanes per task: every lane of a warp runs the block update when any task of the
+                    // warp has work (the lane pairs exchange values by shuffles); lanes without work compute on
+                    // harmless cells and commit nothing
+                    const int h = tid & 1;
+                    int xb = -2 * j;
+                    int m = j - QS * g;
+                    // amplitudes of the block (row-major plane in global memory, read-only), fetched one macro-step ahead
+                    double ampn[SBK];
+                    auto fetch_amp = [&](int xb_, int m_) {
+                        const bool valid_ = has_slot && g < Gp && xb_ >= 0 && xb_ < nb_my && m_ >= 0 && m_ < T;
+                        if (valid_) {
+                            const double2 *ap = reinterpret_cast<const double2 *>(v.A + (grow0 + m_ + Q - 1) * P + v.c0 + b0 + SBK * xb_);
+#pragma unroll
+                            for (int q = 0; q < SBK / 2; ++q) {
+                                const double2 a2 = __ldg(ap + q);
+                                ampn[2 * q] = a2.x; ampn[2 * q + 1] = a2.y;
+                            }
+                        }
+                    };
+                    fetch_amp(xb, m);
+                    cta_sync();
+                    for (int t = 0; t < nsteps; ++t) {
+                        const long long k0 = clock64();
+                        if ((t & 1) == 0) {
+                            const int k = t >> 1;
+                            const int e_lo = k == 0 ? 0 : k + 2 * (Q - 1), e_hi = k + 2 * (Q - 1);
+                            for (int e = e_lo; e <= e_hi && e < Tp; ++e) {
+                                unsigned spins = 0;
+                                while (!mbar_try_wait(&mbar[e % R], (unsigned)((e / R) & 1)))
+                                    if (!keep_waiting(spins, prm.status, 0x30000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
+                            }
+                        }
+                        const bool valid = has_slot && g < Gp && xb >= 0 && xb < nb_my && m >= 0 && m < T;
+                        const int e = valid ? m + Q - 1 : Q - 1;
+                        const int xbv = valid ? xb : 0;
+                        const int n0 = b0 + SBK * xbv;
+                        double amp[SBK];
+                        unsigned active = 0;
+#pragma unroll
+                        for (int i = 0; i < SBK; ++i) {
+                            amp[i] = valid ? ampn[i] : 0.0;
+                            if (valid && n0 + i < Nreal && amp[i] > thr) active |= 1u << i; // lwslib.cpp:295-296
+                        }
+                        // next macro-step's task of this slot
+                        int xb1 = xb + 1, m1 = m;
+                        if (xb1 == NBV) { xb1 = 0; m1 += NS; }
+                        fetch_amp(xb1, m1);
+                        if (__any_sync(0xffffffffu, active != 0)) {
+                            PairCell<Q> cell;
+                            cell.base = ring + 8 * h;
+                            const int es = e % R;
+#pragma unroll
+                            for (int d = 0; d < 2 * Q - 1; ++d) {
+                                int sl = es + d - (Q - 1);
+                                sl = sl < 0 ? sl + R : (sl >= R ? sl - R : sl);
+                                cell.rowoff[d] = (unsigned)sl * rowbytes;
+                            }
+                            cell.col0 = SL + SBK * xbv;
+                            BlockCtx bc;
+                            bc.ring = ring; bc.ring_left = ring_left; bc.ring_right = ring_right;
+                            bc.ownoff = cell.rowoff[Q - 1]; bc.xb = xbv; bc.n0 = n0; bc.b0 = b0;
+                            bc.Nreal = Nreal; bc.NBr = NBr; bc.first_strip = (c == 0);
+                            pair_update_block<Q, FOLD, PAT, (PAIR - 1) % 3, (PAIR - 1) / 3>(cell, w, bc, amp, active, h);
+                        }
+                        const long long k1 = clock64();
+                        cta_sync(); // macro-step t done
+                        xb = xb1; m = m1;
+                        const long long k2 = clock64();
+                        cta_sync(); // neighbours ready for macro-step t + 1
+                        tm_work += k1 - k0; tm_waitA += k2 - k1; tm_waitB += clock64() - k2;
+                    }
                 } else {
                 int xb = -2 * j;          // block index; negative while the slot has not started
                 int m = j - QS * g;       // frame of the slot
@@ -1003,15 +1108,47 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------- self-check of the branch-free sqrt / division
+// Inputs: a 64-bit mix of the index (every exponent from 2^-1022 to 2^1023 and signs on the numerator); counts
+// the samples inside the fast ranges and those among them whose bits differ from __dsqrt_rn / __ddiv_rn.
+__global__ void k_debug_fast_math(long long n, unsigned long long seed, unsigned long long *out)
+{
+    unsigned long long chk_s = 0, bad_s = 0, chk_d = 0, bad_d = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        auto mix = [](unsigned long long z) {
+            z += 0x9e3779b97f4a7c15ull; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31);
+        };
+        const unsigned long long a = mix(seed + 2 * (unsigned long long)i), b = mix(seed + 2 * (unsigned long long)i + 1);
+        // half the samples: exponents near 1 (the values the sweeps see), half: any exponent
+        const bool wide = (i & 1) != 0;
+        auto make = [&](unsigned long long bits, bool neg_ok) {
+            unsigned long long e = (bits >> 52) & 0x7ff;
+            if (!wide) e = 1023 - 40 + e % 80;
+            if (e == 0x7ff) e = 0x7fe;
+            unsigned long long v = (bits & 0x000fffffffffffffull) | (e << 52);
+            if (neg_ok && (bits >> 63)) v |= 1ull << 63;
+            return __longlong_as_double((long long)v);
+        };
+        const double x = make(a, false), num = (i % 97 == 0) ? 0.0 : make(b, true);
+        bool sok, rok, dok;
+        const double s = fm_sqrt(x, sok);
+        if (sok) { ++chk_s; if (__double_as_longlong(s) != __double_as_longlong(__dsqrt_rn(x))) ++bad_s; }
+        const double q = fm_div(num, x, fm_rcp(x, rok), dok);
+        if (rok && dok) { ++chk_d; if (__double_as_longlong(q) != __double_as_longlong(__ddiv_rn(num, x))) ++bad_d; }
+    }
+    atomicAdd(out + 0, chk_s); atomicAdd(out + 1, bad_s); atomicAdd(out + 2, chk_d); atomicAdd(out + 3, bad_d);
+}
+
 } // namespace
 
 // ---------------------------------------------------------------- host side
 namespace {
 
-template <int Q, int FOLD, int PAT, bool TM>
+template <int Q, int FOLD, int PAT, bool TM, int PAIR = 0, int NREG = 255>
 cudaError_t launch_strips_t(const StripParams &prm, const StripW<Q> &w, const StripPlan &pl, int B, cudaStream_t s)
 {
-    auto kern = k_batch_strips<Q, FOLD, PAT, TM>;
+    auto kern = k_batch_strips<Q, FOLD, PAT, TM, PAIR, NREG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
     if (e != cudaSuccess) return e;
     if (pl.C > 8) {
@@ -1033,6 +1170,51 @@ cudaError_t launch_strips_t(const StripParams &prm, const StripW<Q> &w, const St
     if (ncl < 1) return cudaErrorLaunchOutOfResources;
     cfg.gridDim = dim3((unsigned)(std::min(ncl, B) * pl.C));
     return cudaLaunchKernelEx(&cfg, kern, prm, w);
+}
+
+// pair-split kernels.  The register file is 16 K registers per SM sub-partition and warps are dealt to the four
+// sub-partitions in turn: up to 8 warps keep 255 registers, 9-12 warps 168, 13-16 warps 128.  Measured on B200 the
+// spills of the smaller caps cost more than the extra warps bring, so the planner stays at
+// 7 task warps + the control warp and only that tier is built (all three with -DLWSB_PAIR_EXPERIMENTS).
+template <int Q, int FOLD, int PAT>
+cudaError_t launch_pair(const StripParams &prm, const StripW<Q> &w, const StripPlan &pl, int B, cudaStream_t s)
+{
+    const int mode = pl.TM - LWSB_VARIANT_PAIR; // window mode + 3 * explicit pipelining
+    const int nt = pl.nthreads;
+#ifdef LWSB_PAIR_EXPERIMENTS
+    if (nt > PAIR_THREADS_MAX) return cudaErrorInvalidValue;
+#define LWSB_PAIR_CASE(M_)                                                                                   \
+    case M_:                                                                                                 \
+        if (nt <= 256) return launch_strips_t<Q, FOLD, PAT, false, M_ + 1, 255>(prm, w, pl, B, s);           \
+        if (nt <= 384) return launch_strips_t<Q, FOLD, PAT, false, M_ + 1, 168>(prm, w, pl, B, s);           \
+        return launch_strips_t<Q, FOLD, PAT, false, M_ + 1, 128>(prm, w, pl, B, s);
+#else
+    if (nt > PAIR_THREADS_PLAN) return cudaErrorInvalidValue;
+#define LWSB_PAIR_CASE(M_)                                                                                   \
+    case M_: return launch_strips_t<Q, FOLD, PAT, false, M_ + 1, 255>(prm, w, pl, B, s);
+#endif
+    switch (mode) {
+        LWSB_PAIR_CASE(LWSB_PAIR_DEFAULT_MODE)
+#ifdef LWSB_PAIR_EXPERIMENTS
+    default:
+        if constexpr (Q == 4 && PAT == 1) {
+            switch (mode) {
+                LWSB_PAIR_CASE((LWSB_PAIR_DEFAULT_MODE + 1) % 6)
+                LWSB_PAIR_CASE((LWSB_PAIR_DEFAULT_MODE + 2) % 6)
+                LWSB_PAIR_CASE((LWSB_PAIR_DEFAULT_MODE + 3) % 6)
+                LWSB_PAIR_CASE((LWSB_PAIR_DEFAULT_MODE + 4) % 6)
+                LWSB_PAIR_CASE((LWSB_PAIR_DEFAULT_MODE + 5) % 6)
+            }
+        }
+#endif
+    }
+#undef LWSB_PAIR_CASE
+    if (mode != LWSB_PAIR_DEFAULT_MODE) { // a mode this build (or this Q / mask) has no kernel for: the default one
+        StripPlan pd = pl;
+        pd.TM = LWSB_VARIANT_PAIR + LWSB_PAIR_DEFAULT_MODE;
+        return launch_pair<Q, FOLD, PAT>(prm, w, pd, B, s);
+    }
+    return cudaErrorInvalidValue;
 }
 
 template <int Q>
@@ -1059,9 +1241,11 @@ cudaError_t launch_strips_q(const StripParams &prm, const double *wr, const doub
                 if (pat_has<Q, 1>(r, k) != (((w.flag[p][r] >> k) & 1u) != 0)) { def = false; break; }
     if constexpr (Q <= 4) {
         if (fold == LWSB_FOLD_ANY) return launch_strips_t<Q, LWSB_FOLD_ANY, 0, false>(prm, w, pl, B, s);
-        const bool tm = def && pl.TM && pl.NS * pl.G <= 128;
+        const bool tm = def && pl.TM == LWSB_VARIANT_TM && pl.NS * pl.G <= 128;
+        const bool pair = pl.TM >= LWSB_VARIANT_PAIR;
         if constexpr (Q == 4) {
             if (fold == LWSB_FOLD_Q4) {
+                if (pair) return def ? launch_pair<4, LWSB_FOLD_Q4, 1>(prm, w, pl, B, s) : launch_pair<4, LWSB_FOLD_Q4, 0>(prm, w, pl, B, s);
                 if (tm) return launch_strips_t<4, LWSB_FOLD_Q4, 1, true>(prm, w, pl, B, s);
                 return def ? launch_strips_t<4, LWSB_FOLD_Q4, 1, false>(prm, w, pl, B, s)
                            : launch_strips_t<4, LWSB_FOLD_Q4, 0, false>(prm, w, pl, B, s);
@@ -1069,6 +1253,7 @@ cudaError_t launch_strips_q(const StripParams &prm, const double *wr, const doub
         }
         if constexpr (Q == 2) {
             if (fold == LWSB_FOLD_Q2) {
+                if (pair) return def ? launch_pair<2, LWSB_FOLD_Q2, 1>(prm, w, pl, B, s) : launch_pair<2, LWSB_FOLD_Q2, 0>(prm, w, pl, B, s);
                 if (tm) return launch_strips_t<2, LWSB_FOLD_Q2, 1, true>(prm, w, pl, B, s);
                 return def ? launch_strips_t<2, LWSB_FOLD_Q2, 1, false>(prm, w, pl, B, s)
                            : launch_strips_t<2, LWSB_FOLD_Q2, 0, false>(prm, w, pl, B, s);
@@ -1085,9 +1270,23 @@ cudaError_t launch_strips_q(const StripParams &prm, const double *wr, const doub
 // Chooses cluster size, strip width and sweeps per pass.  Returns false when the shape is not
 // served by this kernel (the generic kernel takes over).
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
-                 int force_cluster, int max_sweeps, int force_lag, int use_tm)
+                 int force_cluster, int max_sweeps, int force_lag, int variant, int fold)
 {
     if (L != SL || !(Q == 2 || Q == 4 || Q == 8) || iters < 1) return false;
+    // variant: the pair-split kernel serves the folded Q = 2 / Q = 4 updates and is the default there
+    const bool pair_ok = (Q == 2 && fold == LWSB_FOLD_Q2) || (Q == 4 && fold == LWSB_FOLD_Q4);
+    int var = variant;
+    // automatic = one thread per task: with the branch-free projection it is as fast as or faster than the pair-split
+    // kernels on every plan measured; those stay selectable
+    if (var == LWSB_VARIANT_AUTO) var = LWSB_VARIANT_SCALAR;
+    if (var >= LWSB_VARIANT_PAIR && (!pair_ok || var > LWSB_VARIANT_PAIR + 5)) var = LWSB_VARIANT_SCALAR;
+#ifndef LWSB_PAIR_EXPERIMENTS
+    if (var >= LWSB_VARIANT_PAIR) var = LWSB_VARIANT_PAIR + LWSB_PAIR_DEFAULT_MODE;
+#endif
+    if (var == LWSB_VARIANT_TM && Q > 4) var = LWSB_VARIANT_SCALAR;
+    const bool tm = var == LWSB_VARIANT_TM;
+    const bool pair = var >= LWSB_VARIANT_PAIR;
+    const int task_cap = tm ? 128 : (pair ? (pair_thread_cap(max_sweeps) - 32) / 2 : 256 - 32);
     const int nbt = (Nreal + SBK - 1) / SBK; // blocks holding real bins
     bool found = false;
     double best = 0.0;
@@ -1111,13 +1310,14 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
         for (int QS = Q; QS <= Q + 1; ++QS) {
             if (Rmax < 2 * Q + SLEAD + NS) continue;
             int Gmax = (Rmax - 2 * Q - SLEAD - NS) / QS + 1;
-            const bool tm = use_tm != 0 && Q <= 4; // producer / consumer warps through tensor memory: 128 tasks per CTA
-            Gmax = std::min(Gmax, (tm ? 128 : 256 - 32) / NS);
+            Gmax = std::min(Gmax, task_cap / NS);
             Gmax = std::min(Gmax, iters);
             if (max_sweeps > 0) Gmax = std::min(Gmax, max_sweeps);
+            if (max_sweeps < -1) Gmax = std::min(Gmax, -max_sweeps); // experiments: negative = sweeps per pass without the pair kernels' thread cap
             for (int G = Gmax; G >= 1 && G > Gmax - 8; --G) {
-                // shared-memory wavefronts per 128-bit warp access: the 8 lanes of a quarter-warp hit
-                // 16-byte bank groups (j - QS*g) mod 8 (odd pitch); the busiest group sets the count
+                // shared-memory wavefronts per warp access: 8 tasks (a quarter-warp of 128-bit accesses, or a
+                // half-warp of lane pairs reading 64 bits each) hit 16-byte bank groups (j - QS*g) mod 8 (odd
+                // pitch); the busiest group sets the count
                 double f = 0.0; int gfast = 0;
                 for (int order = 0; order < 2; ++order) {
                     double waves = 0.0; int quarters = 0;
@@ -1134,17 +1334,20 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                 if (force_lag > 0 && QS != force_lag) continue;
                 const int npass = (iters + G - 1) / G;
                 const double steps = 2.0 * (maxT + QS * G) + NBV + (C - 1) * NBr;
-                // Cost model fitted on B200: a macro-step costs ~15k cycles of dependent
-                // fp64 latency plus ~1.1k per compute warp and shared-memory wavefront factor (measured over
-                // cluster sizes 2-8, 4-6 warps, conflict factors 1.0-2.0); a pass adds a fixed prologue.
-                const int cwarps = (NS * G + 31) / 32;
-                const double t_step = 15000.0 + 1100.0 * cwarps * f + (C > 2 ? 800.0 : 0.0);
+                // Cost models fitted on B200.  One thread per task, branch-free projection: a
+                // macro-step costs ~6k cycles plus ~1.3k per compute warp and shared-memory wavefront factor
+                // (measured over cluster sizes 2-8, 3-6 warps, conflict factors 1.0-1.75; 11.5k-19.5k cycles).
+                // Pair-split: half the instructions per warp and twice the warps.  A pass adds a fixed prologue.
+                const int cwarps = ((pair ? 2 : 1) * NS * G + 31) / 32;
+                const double t_step = pair ? PAIR_T0 + PAIR_T1 * cwarps * (1.0 + PAIR_TF * (f - 1.0)) + (C > 2 ? 800.0 : 0.0)
+                                           : 6000.0 + 1300.0 * cwarps * f + (C > 2 ? 300.0 : 0.0) + (C > 4 ? 1700.0 : 0.0);
                 const double cost = rounds * npass * (steps * t_step + 60000.0);
                 if (!found || cost < best) {
                     found = true; best = cost;
-                    out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast; out->TM = tm ? 1 : 0;
+                    out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast;
+                    out->TM = tm ? LWSB_VARIANT_TM : (pair ? var : 0);
                     out->R = QS * (G - 1) + 2 * Q + SLEAD + NS;
-                    out->nthreads = (NS * G + 31) / 32 * 32 + 32;
+                    out->nthreads = ((pair ? 2 : 1) * NS * G + 31) / 32 * 32 + 32;
                     out->smem_bytes = (int)(fixed + (size_t)out->R * (rowbytes + 8));
                 }
             }
@@ -1173,6 +1376,12 @@ cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const 
     case 8: return launch_strips_q<8>(prm, wr_host, wi_host, fold, pl, v.B, s);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_debug_fast_math(long long n, unsigned long long seed, unsigned long long *out4, cudaStream_t s)
+{
+    k_debug_fast_math<<<296, 256, 0, s>>>(n, seed, out4);
+    return cudaGetLastError();
 }
 
 } // namespace lwsb

@@ -311,3 +311,62 @@ def test_strip_kernel_tensor_memory_variant(gpu, oracle, fs, hop, n, its, cluste
     finally:
         ctx.set_tuning(0, 0, 0)
         ctx.set_variant(0, 0)
+
+
+PAIR_CASES = [(512, 128, 9000, 9, 2, 0), (512, 128, 9000, 9, 4, 5), (1024, 256, 30000, 12, 2, 0), (1024, 256, 30000, 12, 8, 0),
+              (128, 64, 9000, 10, 1, 0), (128, 64, 9000, 10, 2, 3), (512, 128, 700, 5, 1, 0)]
+
+
+@pytest.mark.parametrize("variant", [2, 10, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("fs,hop,n,its,cluster,lag", PAIR_CASES)
+def test_strip_kernel_variants(gpu, oracle, variant, fs, hop, n, its, cluster, lag):
+    """One thread per task (2) and the pair-split kernels (10 + window mode + 3 * explicit pipelining; modes that are
+    not compiled into this build fall back to the default one): same bits, default and custom windows."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(fs, hop), gpu.lws(fs, hop)
+    A = np.abs(po.stft(make_signal("tonal", 4, n)))
+    try:
+        ctx.set_tuning(0, cluster, 0)
+        ctx.set_variant(lag, variant)
+        for thr in (np.zeros(its), gpu.get_thresholds(its, 2.0, 0.1, 1)):
+            Y = pg.batch_lws(A, thresholds=thr)
+            plan = ctx.last_batch_plan()
+            assert plan is not None and plan["cluster"] == cluster
+            assert (plan["tensor_memory"] == 0) == (variant == 2), plan
+            assert plan["threads"] <= 256
+            assert lag == 0 or plan["sweep_lag"] == lag
+            _close(Y, po.batch_lws(A, thresholds=thr), "variant %d %s" % (variant, plan))
+    finally:
+        ctx.set_tuning(0, 0, 0)
+        ctx.set_variant(0, 0)
+
+
+@pytest.mark.parametrize("variant", [2, 13, 14])
+def test_strip_kernel_variants_custom_window_and_complex_input(gpu, oracle, variant):
+    """A window whose |W| > 1e-12 mask differs from the default pattern (run-time mask path) and a complex input."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    g = golden("custom_win")
+    case = [c for c in CASES if c["name"] == "custom_win"][0]
+    po, pg = _ctor(oracle, case), _ctor(gpu, case)
+    rng = np.random.default_rng(11)
+    X = g["X"]
+    S = np.abs(X) * np.exp(1j * rng.uniform(-np.pi, np.pi, X.shape))
+    try:
+        ctx.set_variant(0, variant)
+        for inp in (np.abs(X), S):
+            for thr in (np.zeros(7), gpu.get_thresholds(7, 2.0, 0.2, 1)):
+                _close(pg.batch_lws(inp, thresholds=thr), po.batch_lws(inp, thresholds=thr), "custom window, variant %d" % variant)
+    finally:
+        ctx.set_variant(0, 0)
+
+
+def test_branch_free_sqrt_and_division_match_the_library(gpu):
+    """The pair-split kernels' sqrt / division (MUFU seed + Newton steps, no slow-path branch) give the bits of
+    __dsqrt_rn / __ddiv_rn on every sample inside their fast ranges (10^8 samples, all exponents)."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    chk_s, bad_s, chk_d, bad_d = ctx.debug_fast_math(100_000_000, 7)
+    assert chk_s > 90_000_000 and chk_d > 50_000_000, (chk_s, chk_d)  # half the division samples have any exponent: many quotients leave the fast range
+    assert bad_s == 0 and bad_d == 0, (bad_s, bad_d)
