@@ -141,6 +141,13 @@ int lwsb_set_tuning(lwsb_ctx *ctx, long long smem_limit, int cluster, int sweeps
  * register-window mode (0..2) + 3 * explicit software pipelining (modes other than the default one exist only in
  * builds with -DLWSB_PAIR_EXPERIMENTS and otherwise select the default).  Results do not depend on it. */
 int lwsb_set_variant(lwsb_ctx *ctx, int sweep_lag, int tensor_memory);
+/* time line of the strip kernel's work items -- one per (utterance, pass); the passes of an utterance run on different
+ * clusters at the same time, each a few frames behind the previous one.  enable != 0 switches recording on for the
+ * following lwsb_batch calls (also: env LWSB_STRIP_TRACE=1); returns the number of items of the last call copied out:
+ * utt_pass[2i], utt_pass[2i+1] and stamps[8i..8i+7] = GPU globaltimer (ns) when the item was taken, its ring primed,
+ * its last macro-step done, its frames written back; then cycles of strip 0: control lane waiting for the previous
+ * pass's rows / polling its neighbours, compute warp 0 at work / waiting for the control warp. */
+int lwsb_last_batch_trace(lwsb_ctx *ctx, int enable, int max_items, int *utt_pass, unsigned long long *stamps);
 /* self-check of the branch-free sqrt / division of the pair-split kernels against the CUDA library functions on
  * n pseudo-random inputs: out4 = {sqrt samples in the fast range, of which differing, division samples, differing} */
 int lwsb_debug_fast_math(lwsb_ctx *ctx, long long n, unsigned long long seed, unsigned long long *out4);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "lwsb_set_tuning": (_ci, [_vp, _ll, _ci, _ci]),
     "lwsb_set_variant": (_ci, [_vp, _ci, _ci]),
     "lwsb_last_batch_cycles": (_ci, [_vp, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "lwsb_last_batch_trace": (_ci, [_vp, _ci, _ci, _ip, ctypes.POINTER(ctypes.c_ulonglong)]),
     "lwsb_debug_fast_math": (_ci, [_vp, _ll, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]),
     "lwsb_debug_online_chain_length": (_ll, [_ci, _ci, _ci]),
     "lwsb_debug_online_task": (_ci, [_ci, _ci, _ci, _ci, _ll, _ip, _ip, _ip, _ip, _ip]),
@@ -262,6 +263,19 @@ class Context(object):
 
     def set_variant(self, sweep_lag=0, tensor_memory=0):
         self._c(lib().lwsb_set_variant(self._h, int(sweep_lag), int(tensor_memory)))
+
+    def batch_trace(self, enable=True, max_items=4096):
+        """Switch the strip kernel's work-item time line on / off and return the one of the last batch() call: list of
+        (utterance, pass, taken, primed, computed, written [ns from the first stamp], cycles of strip 0: control lane
+        waiting for rows / polling neighbours, compute warp 0 working / waiting for the control warp)."""
+        up = (ctypes.c_int * (2 * max_items))()
+        st = (ctypes.c_ulonglong * (8 * max_items))()
+        n = self._c(lib().lwsb_last_batch_trace(self._h, 1 if enable else 0, max_items, up, st))
+        if n <= 0:
+            return []
+        t0 = min(st[8 * i] for i in range(n))
+        return [(up[2 * i], up[2 * i + 1]) + tuple(int(st[8 * i + k]) - t0 for k in range(4)) + tuple(int(st[8 * i + k]) for k in range(4, 8))
+                for i in range(n)]
 
     def debug_fast_math(self, n, seed=1):
         """(sqrt samples checked, differing, division samples checked, differing) of the kernels' branch-free sqrt / division."""

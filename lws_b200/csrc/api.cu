@@ -63,6 +63,10 @@ struct lwsb_ctx {
     std::map<long long, std::pair<int, int>> stat_index; // array length -> (first leaf, leaf count)
     DevBuf fx, fS, fwin, fframes;          // stft / istft staging
     DevBuf status;                         // watchdog word of the strip kernel
+    DevBuf items, done, trace;             // strip kernel: (utterance, pass) work list, per-strip progress counters, optional time stamps
+    bool want_trace = false;               // env LWSB_STRIP_TRACE=1 / lwsb_last_batch_trace
+    int trace_items = 0;
+    std::vector<int> trace_list;
     int last_kernel = 0;                   // 0 generic, 1 strips (introspection)
     long long tune_smem = 0;               // tuning knobs (lwsb_set_tuning): shared-memory budget, cluster size,
     int tune_cluster = 0, tune_sweeps = 0; // sweeps per pass; 0 = automatic
@@ -187,6 +191,7 @@ extern "C" int lwsb_create(int device, void *stream, lwsb_ctx **out)
     if (const char *e3 = getenv("LWSB_STRIP_SWEEPS")) c->tune_sweeps = atoi(e3);
     if (const char *e4 = getenv("LWSB_STRIP_LAG")) c->tune_lag = atoi(e4);
     if (const char *e5 = getenv("LWSB_STRIP_TM")) c->tune_tm = atoi(e5);
+    if (const char *e6 = getenv("LWSB_STRIP_TRACE")) c->want_trace = atoi(e6) != 0;
     *out = c;
     return LWSB_OK;
 }
@@ -196,7 +201,7 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
     CHECK_CTX(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->E, &c->A, &c->row_max, &c->leaf_tab, &c->tab_of, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
+    for (DevBuf *b : {&c->items, &c->done, &c->trace, &c->E, &c->A, &c->row_max, &c->leaf_tab, &c->tab_of, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
                       &c->drowbase, &c->stage, &c->dptr, &c->dthr, &c->flags, &c->fx, &c->fS, &c->fwin, &c->fframes, &c->status})
         b->release();
     for (auto &kv : c->twiddles) kv.second.release();
@@ -410,15 +415,18 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
     // sweeps whose threshold is not below max|S| cannot move a bin (lwslib.cpp:295-296): the strip kernel drops
     // them, and the plan is sized for the number that remain (largest over the batch)
     int active = iterations;
+    std::vector<int> nact; // sweeps per utterance that can move a bin
     if (!(flags & LWSB_FORCE_GENERIC)) {
         std::vector<double> mean(c->B), mx(c->B);
         CU(c, cudaMemcpyAsync(mean.data(), c->mean_amp.p, c->B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(mx.data(), c->max_amp.p, c->B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
         active = 0;
+        nact.resize(c->B);
         for (int b = 0; b < c->B; ++b) {
             int n = 0;
             for (int i = 0; i < iterations; ++i) n += (thresholds[i] * mean[b] < mx[b]) ? 1 : 0;
+            nact[b] = n;
             active = std::max(active, n);
         }
         active = std::max(active, 1);
@@ -433,10 +441,37 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
     if (strips) {
         CU(c, c->status.reserve(256));
         CU(c, cudaMemsetAsync(c->status.p, 0, 256, c->stream));
+        // work list: one item per (utterance, pass of pl.G sweeps), pass-major, so that the passes of one utterance
+        // run on different clusters at the same time, each a few frames behind the previous one
+        std::vector<int> items;
+        int max_pass = 0;
+        for (int pass = 0, more = 1; more; ++pass) {
+            more = 0;
+            for (int b = 0; b < c->B; ++b)
+                if (pass * pl.G < nact[b]) { items.push_back(b); items.push_back(pass); more = 1; max_pass = pass + 1; }
+        }
+        const int n_items = (int)(items.size() / 2);
+        const size_t done_bytes = (size_t)c->B * std::max(max_pass, 1) * STRIP_MAX_CLUSTER * sizeof(unsigned);
+        if (n_items > 0) {
+            CU(c, c->items.reserve(items.size() * sizeof(int)));
+            CU(c, c->done.reserve(done_bytes));
+            CU(c, cudaMemcpyAsync(c->items.p, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            CU(c, cudaMemsetAsync(c->done.p, 0, done_bytes, c->stream));
+        }
+        c->trace_items = 0;
+        if (c->want_trace && n_items > 0) {
+            CU(c, c->trace.reserve((size_t)n_items * 8 * sizeof(unsigned long long)));
+            CU(c, cudaMemsetAsync(c->trace.p, 0, (size_t)n_items * 8 * sizeof(unsigned long long), c->stream));
+            c->trace_items = n_items;
+            c->trace_list = items;
+        }
         if (int r = begin_compute(c)) return r;
-        CU(c, launch_batch_strips(c->view(), c->w[LWSB_W].wr.data(), c->w[LWSB_W].wi.data(), fold,
-                                  c->dthr.as<const double>(), c->max_amp.as<const double>(), iterations, pl,
-                                  c->status.as<unsigned>(), c->stream));
+        if (n_items > 0) {
+            CU(c, launch_batch_strips(c->view(), c->w[LWSB_W].wr.data(), c->w[LWSB_W].wi.data(), fold,
+                                      c->dthr.as<const double>(), c->max_amp.as<const double>(), iterations, pl,
+                                      c->status.as<unsigned>(), c->items.as<const int>(), n_items, max_pass, c->done.as<unsigned>(),
+                                      c->want_trace ? c->trace.as<unsigned long long>() : nullptr, c->stream));
+        }
         c->launches += 1;
         c->last_kernel = 1; c->last_plan = pl;
         if (int r = end_compute(c)) return r;
@@ -734,6 +769,19 @@ extern "C" int lwsb_last_batch_cycles(lwsb_ctx *c, unsigned long long *out7)
     CU(c, cudaMemcpyAsync(out7, c->status.as<char>() + 8, 13 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return 1;
+}
+
+extern "C" int lwsb_last_batch_trace(lwsb_ctx *c, int enable, int max_items, int *utt_pass, unsigned long long *stamps)
+{
+    CHECK_CTX(c);
+    c->want_trace = enable != 0;
+    if (!utt_pass || !stamps || max_items <= 0 || c->trace_items == 0 || c->last_kernel != 1) return 0;
+    if (int r = use_device(c)) return r;
+    const int n = std::min(max_items, c->trace_items);
+    CU(c, cudaMemcpyAsync(stamps, c->trace.p, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2 * n; ++i) utt_pass[i] = c->trace_list[i];
+    return n;
 }
 
 extern "C" int lwsb_debug_fast_math(lwsb_ctx *c, long long n, unsigned long long seed, unsigned long long *out4)

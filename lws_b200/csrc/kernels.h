@@ -35,6 +35,7 @@ void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, in
 
 // kernels_batch.cu
 struct StripPlan {
+    int smem_limit; // shared-memory budget the plan was made for
     int C, NBr, NBV, NS, G, R, pitch, nthreads, smem_bytes, QS, GFAST, TM; // TM: 0 one thread per task, LWSB_VARIANT_TM, LWSB_VARIANT_PAIR + window mode
 };
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
@@ -42,7 +43,9 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
 int strips_min_pitch(int Nreal, int c0);
 cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const double *wi_host, int fold,
                                 const double *thr, const double *max_amp, int iters, const StripPlan &pl,
-                                unsigned *status, cudaStream_t s);
+                                unsigned *status, const int *items, int n_items, int max_pass, unsigned *done, unsigned long long *trace,
+                                cudaStream_t s);
+constexpr int STRIP_MAX_CLUSTER = 8; // stride of the per-utterance progress counters
 
 cudaError_t launch_debug_fast_math(long long n, unsigned long long seed, unsigned long long *out4, cudaStream_t s);
 

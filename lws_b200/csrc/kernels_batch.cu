@@ -43,7 +43,8 @@ namespace {
 constexpr int SL = 5;          // stencil reach in bins this kernel is specialised for (L)
 constexpr int SBK = 8;         // bins per block
 constexpr int SLEAD = 2;       // frames of TMA look-ahead
-constexpr unsigned SPIN_LIMIT = 1u << 22; // polls before a wait is declared dead (~0.5 s)
+constexpr unsigned SPIN_LIMIT = 1u << 24; // polls before a wait is declared dead (seconds)
+constexpr unsigned PASS_SPIN_LIMIT = 1u << 27; // waits for another cluster's pass: it may still be busy with earlier work items
 #ifdef LWSB_PAIR_EXPERIMENTS
 constexpr int pair_thread_cap(int max_sweeps) { return max_sweeps < 0 ? 512 : 256; }
 #else
@@ -72,6 +73,15 @@ struct StripParams {
     int iters;
     int C, NBr, NBV, NS, G, R, pitch, QS, GFAST;
     unsigned *status;          // [0]: 0 ok, else first watchdog code
+    // work list: one item per (utterance, pass), pass-major; cluster k takes items k, k + #clusters, ...  A pass reads
+    // each frame after the previous pass of the same utterance -- possibly running on another cluster at the
+    // same time -- has written it back: done[((u * max_pass) + pass) * 8 + strip] counts the frames that pass has
+    // written so far (one writer per counter: the counters only grow)
+    const int2 *items;
+    int n_items, max_pass;
+    unsigned *done;
+    unsigned long long *trace; // optional [n_items][8]: globaltimer stamps (ns) item taken, ring primed, last macro-step done, written back;
+                               // cycles of strip 0: control lane in row waits / neighbour polls, compute warp 0 at work / waiting for the control warp
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -134,6 +144,25 @@ __device__ __forceinline__ void st_release_cluster(unsigned *p, unsigned v)
 {
     asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// all but the most recent bulk store of this thread have been written to global memory
+__device__ __forceinline__ void tma_store_wait_all_but_one() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 
 // CTA-wide barrier usable from the role-split (control / compute) code paths
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1;" ::: "memory"); }
@@ -733,8 +762,13 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
 
     bool mbar_live = false;
     long long tm_publish = 0, tm_poll = 0, tm_house = 0, tm_work = 0, tm_waitA = 0, tm_waitB = 0; // cycle counters (status[2..])
+    long long tm_rows = 0;                                                                        // control lane: waiting for another pass's rows
     long long ph[6] = {0, 0, 0, 0, 0, 0}; // consumer phases of the TM kernels: set-up, own terms, wait A, chain A, wait B, chain B
-    for (int u = cid; u < v.B; u += ncl) {
+    for (int item = cid; item < prm.n_items; item += ncl) {
+        const int u = prm.items[item].x, pass = prm.items[item].y;
+        const bool tracer = prm.trace != nullptr && c == 0 && tid == 0;
+        if (tracer) prm.trace[8 * item + 0] = global_ns();
+        const long long it_rows0 = tm_rows, it_poll0 = tm_poll, it_work0 = tm_work, it_wait0 = tm_waitB;
         const int T = v.T[u];
         const int Tp = T + 2 * (Q - 1);
         const long long grow0 = v.rowbase[u];
@@ -749,13 +783,33 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
         }
         __syncthreads();
         const int n_act = *nact;
-        const int npass = (n_act + G - 1) / G;
-        for (int pass = 0; pass < npass; ++pass) {
+        {
             const int Gp = min(G, n_act - pass * G);
             const int nsteps = 2 * (T - 1 + QS * (Gp - 1)) + NBV;
             const double thr = (has_slot && g < Gp) ? __dmul_rn(prm.thr[act[pass * G + g]], mean) : 0.0; // lws.pyx:245
 
-            // ---- pass prologue: previous pass fully written back everywhere, ring (re)initialised
+            // Row e may be loaded once the previous pass of this utterance -- on this or on another cluster -- has
+            // written it back in the three strips the load spans (ghost frames are never rewritten).
+            auto wait_rows = [&](int e) {
+                const int mf = e - (Q - 1);
+                if (pass == 0 || mf < 0 || mf >= T) return;
+                const long long w0 = clock64();
+                const unsigned need = (unsigned)(mf + 1);
+                const unsigned *prev = prm.done + ((size_t)u * prm.max_pass + (pass - 1)) * 8;
+                for (int cc = max(c - 1, 0); cc <= min(c + 1, C - 1); ++cc) {
+                    unsigned spins = 0;
+                    while (ld_acquire_gpu(prev + cc) < need) {
+                        __nanosleep(64);
+                        if ((++spins & 1023u) == 0) {
+                            if (*reinterpret_cast<volatile unsigned *>(prm.status) != 0u) break;
+                            if (spins > PASS_SPIN_LIMIT) { atomicCAS(prm.status, 0u, 0x40000000u | (c << 24) | ((pass & 0xff) << 16) | (e & 0xffff)); break; }
+                        }
+                    }
+                }
+                fence_proxy_async();
+                tm_rows += clock64() - w0;
+            };
+            // ---- pass prologue: this cluster's previous work item fully written back, ring (re)initialised
             if (ctl) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
             cluster.sync();
             if (ctl) {
@@ -768,11 +822,13 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                 fence_proxy_async();
                 const int npre = min(Tp, 2 * (Q - 1) + SLEAD + 1);
                 for (int e = 0; e < npre; ++e) {
+                    wait_rows(e);
                     mbar_expect_tx(&mbar[e % R], load_bytes);
                     tma_load_row(ring + (size_t)(e % R) * rowbytes, v.E + (grow0 + e) * P + gcol0, load_bytes, &mbar[e % R]);
                 }
             }
             cluster.sync();
+            if (tracer) prm.trace[8 * item + 1] = global_ns();
 
             // ---- control actions (executed by the thread `ctl` only)
             auto poll = [&](int t) { // conditions for macro-step t (DESIGN.md "strip hand-shake")
@@ -806,6 +862,7 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                     const int e = (t + 1) / 2 + 2 * (Q - 1) + SLEAD;
                     if (e < Tp) {
                         tma_store_wait_read(); // bulk stores issued a macro-step or more ago: long finished reading
+                        wait_rows(e);
                         fence_proxy_async();
                         mbar_expect_tx(&mbar[e % R], load_bytes);
                         tma_load_row(ring + (size_t)(e % R) * rowbytes, v.E + (grow0 + e) * P + gcol0, load_bytes, &mbar[e % R]);
@@ -819,6 +876,9 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                         fence_proxy_async();
                         tma_store_row(v.E + (grow0 + e) * P + gcol0 + wb_lo,
                                       ring + (size_t)(e % R) * rowbytes + (size_t)wb_lo * 16u, (unsigned)(wb_hi - wb_lo) * 16u);
+                        // frames 0 .. m-1 of this pass are in global memory: tell the next pass of this utterance
+                        tma_store_wait_all_but_one();
+                        if (m >= 1) { fence_proxy_async(); __threadfence(); st_release_gpu(prm.done + ((size_t)u * prm.max_pass + pass) * 8 + c, (unsigned)m); }
                     }
                 }
             };
@@ -1087,8 +1147,18 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                 }
             }
         }
-        // ---- utterance epilogue: everything written back before the ring is reused
-        if (ctl) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); }
+        // ---- item epilogue: everything written back before the ring is reused; the pass is complete
+        if (tracer) prm.trace[8 * item + 2] = global_ns();
+        if (ctl) { tma_store_wait_all(); fence_proxy_async(); __threadfence(); st_release_gpu(prm.done + ((size_t)u * prm.max_pass + pass) * 8 + c, (unsigned)T); }
+        if (prm.trace != nullptr && c == 0 && ctl) {
+            prm.trace[8 * item + 3] = global_ns();
+            prm.trace[8 * item + 4] = (unsigned long long)(tm_rows - it_rows0);
+            prm.trace[8 * item + 5] = (unsigned long long)(tm_poll - it_poll0);
+        }
+        if (tracer) {
+            prm.trace[8 * item + 6] = (unsigned long long)(tm_work - it_work0);
+            prm.trace[8 * item + 7] = (unsigned long long)(tm_waitB - it_wait0);
+        }
     }
     // cycle accounting of cluster 0 (introspection: lwsb_last_batch_cycles): control lane and one lane per compute warp
     if (cid == 0 && lane == 0) {
@@ -1155,9 +1225,17 @@ cudaError_t launch_strips_t(const StripParams &prm, const StripW<Q> &w, const St
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
     }
+    // one CTA per SM: small plans (short rings) would otherwise share an SM while other SMs idle, and the passes of
+    // one utterance -- a dependency chain across clusters -- would slow each other down
+    int dev = 0, smem_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    const int smem_launch = std::max(pl.smem_bytes, std::min(smem_sm / 2 + 1024, pl.smem_limit));
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_launch);
+    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(TM ? 256 : pl.nthreads);
-    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.dynamicSmemBytes = smem_launch;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1168,7 +1246,7 @@ cudaError_t launch_strips_t(const StripParams &prm, const StripW<Q> &w, const St
     e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
     if (e != cudaSuccess) return e;
     if (ncl < 1) return cudaErrorLaunchOutOfResources;
-    cfg.gridDim = dim3((unsigned)(std::min(ncl, B) * pl.C));
+    cfg.gridDim = dim3((unsigned)(std::min(ncl, prm.n_items) * pl.C)); // all clusters resident: a pass may wait for another cluster's
     return cudaLaunchKernelEx(&cfg, kern, prm, w);
 }
 
@@ -1305,7 +1383,6 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
         if (smem_limit < fixed + rowbytes * 8) continue;
         const int Rmax = (int)((smem_limit - fixed) / (rowbytes + 8));
         const int ncl = std::max(1, (sm_count * 9 / 10) / C); // GPC packing loses a few SMs to clusters
-        const double rounds = std::ceil((double)B / ncl);
         // sweep lag: Q frames is the minimum; an odd lag lets the sweep-fastest thread order be bank-conflict free
         for (int QS = Q; QS <= Q + 1; ++QS) {
             if (Rmax < 2 * Q + SLEAD + NS) continue;
@@ -1314,7 +1391,7 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
             Gmax = std::min(Gmax, iters);
             if (max_sweeps > 0) Gmax = std::min(Gmax, max_sweeps);
             if (max_sweeps < -1) Gmax = std::min(Gmax, -max_sweeps); // experiments: negative = sweeps per pass without the pair kernels' thread cap
-            for (int G = Gmax; G >= 1 && G > Gmax - 8; --G) {
+            for (int G = Gmax; G >= 1; --G) {
                 // shared-memory wavefronts per warp access: 8 tasks (a quarter-warp of 128-bit accesses, or a
                 // half-warp of lane pairs reading 64 bits each) hit 16-byte bank groups (j - QS*g) mod 8 (odd
                 // pitch); the busiest group sets the count
@@ -1339,9 +1416,16 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                 // (measured over cluster sizes 2-8, 3-6 warps, conflict factors 1.0-1.75; 11.5k-19.5k cycles).
                 // Pair-split: half the instructions per warp and twice the warps.  A pass adds a fixed prologue.
                 const int cwarps = ((pair ? 2 : 1) * NS * G + 31) / 32;
+                // per-warp cost scales with the terms per bin: 6 (Q = 2), 17 (Q = 4, folded), 74 (Q = 8)
+                const double tscale = Q == 2 ? 0.4 : (Q == 4 ? 1.0 : 4.3);
                 const double t_step = pair ? PAIR_T0 + PAIR_T1 * cwarps * (1.0 + PAIR_TF * (f - 1.0)) + (C > 2 ? 800.0 : 0.0)
-                                           : 6000.0 + 1300.0 * cwarps * f + (C > 2 ? 300.0 : 0.0) + (C > 4 ? 1700.0 : 0.0);
-                const double cost = rounds * npass * (steps * t_step + 60000.0);
+                                           : 6000.0 + 1300.0 * tscale * cwarps * f + (C > 2 ? 300.0 : 0.0) + (C > 4 ? 1700.0 : 0.0);
+                // work items = (utterance, pass) pairs dealt to the resident clusters in turn
+                // throughput bound, and the critical path of one utterance: its passes run concurrently on different
+                // clusters, each `lag` macro-steps behind the previous one (it reads what that one has written back)
+                const double lag = 2.0 * (Q + SLEAD + QS * (G - 1)) + NBV + 2 + (C - 1) * NBr;
+                const double cost = std::max(std::ceil((double)B * npass / ncl) * (steps * t_step + 60000.0),
+                                             (steps + (npass - 1) * lag) * t_step + 60000.0);
                 if (!found || cost < best) {
                     found = true; best = cost;
                     out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast;
@@ -1349,6 +1433,7 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                     out->R = QS * (G - 1) + 2 * Q + SLEAD + NS;
                     out->nthreads = ((pair ? 2 : 1) * NS * G + 31) / 32 * 32 + 32;
                     out->smem_bytes = (int)(fixed + (size_t)out->R * (rowbytes + 8));
+                    out->smem_limit = (int)smem_limit;
                 }
             }
         }
@@ -1364,9 +1449,11 @@ int strips_min_pitch(int Nreal, int c0)
 
 cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const double *wi_host, int fold,
                                 const double *thr, const double *max_amp, int iters, const StripPlan &pl,
-                                unsigned *status, cudaStream_t s)
+                                unsigned *status, const int *items, int n_items, int max_pass, unsigned *done, unsigned long long *trace,
+                                cudaStream_t s)
 {
     StripParams prm;
+    prm.items = reinterpret_cast<const int2 *>(items); prm.n_items = n_items; prm.max_pass = max_pass; prm.done = done; prm.trace = trace;
     prm.v = v; prm.thr = thr; prm.max_amp = max_amp; prm.iters = iters;
     prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch; prm.QS = pl.QS; prm.GFAST = pl.GFAST;
     prm.status = status;
