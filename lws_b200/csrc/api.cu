@@ -11,6 +11,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <mutex>
 #include <vector>
 
 #include "../../include/lws_b200.h"
@@ -39,6 +40,12 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
+
+std::mutex &strip_mutex(int device)
+{
+    static std::mutex m[64];
+    return m[(unsigned)device % 64u];
+}
 
 } // namespace
 
@@ -465,14 +472,17 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
             c->trace_items = n_items;
             c->trace_list = items;
         }
+        // One strip kernel at a time per device: its clusters wait for one another (a pass reads what the previous
+        // pass of the utterance wrote), which is dead-lock free only while every cluster of the launch is resident.
+        std::lock_guard<std::mutex> strip_guard(strip_mutex(c->device));
         if (int r = begin_compute(c)) return r;
         if (n_items > 0) {
             CU(c, launch_batch_strips(c->view(), c->w[LWSB_W].wr.data(), c->w[LWSB_W].wi.data(), fold,
                                       c->dthr.as<const double>(), c->max_amp.as<const double>(), iterations, pl,
                                       c->status.as<unsigned>(), c->items.as<const int>(), n_items, max_pass, c->done.as<unsigned>(),
                                       c->want_trace ? c->trace.as<unsigned long long>() : nullptr, c->stream));
+            c->launches += 1;
         }
-        c->launches += 1;
         c->last_kernel = 1; c->last_plan = pl;
         if (int r = end_compute(c)) return r;
         unsigned st = 0;

@@ -17,6 +17,7 @@
 // wherever the calling kernel keeps it (global memory or a shared-memory ring).
 #pragma once
 #include <cuda_runtime.h>
+#include "fast_math.cuh"
 #include "lwsb_common.h"
 
 namespace lwsb {
@@ -148,13 +149,24 @@ __device__ __forceinline__ void x_weighted_sum(const Acc &E, const LwsbW &w, int
     }
 }
 
-// lwslib.cpp:355-360: returns false when |t| == 0 (the bin keeps its value)
+// lwslib.cpp:355-360: returns false when |t| == 0 (the bin keeps its value).  sqrt and the two divisions are
+// correctly rounded, like the reference's; they are computed without the library functions' slow-path branches
+// (fast_math.cuh: one basic block, one reciprocal for both divisions), the rare operand outside the fast ranges
+// falls back to the library functions.
 __device__ __forceinline__ bool x_project(double tr, double ti, double a, double2 &out)
 {
-    const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(tr, tr), __dmul_rn(ti, ti)));
-    if (!(mag > 0.0)) return false;
-    out = make_double2(__ddiv_rn(__dmul_rn(tr, a), mag), __ddiv_rn(__dmul_rn(ti, a), mag));
-    return true;
+    const double x = __dadd_rn(__dmul_rn(tr, tr), __dmul_rn(ti, ti));
+    const double nr = __dmul_rn(tr, a), ni = __dmul_rn(ti, a);
+    bool sok, rok, dok1, dok2;
+    double mag = fm_sqrt(x, sok);
+    const double rcp = fm_rcp(mag, rok);
+    out.x = fm_div(nr, mag, rcp, dok1);
+    out.y = fm_div(ni, mag, rcp, dok2);
+    if (!(x == 0.0) && !(sok && rok && dok1 && dok2)) {
+        mag = __dsqrt_rn(x);
+        out.x = __ddiv_rn(nr, mag); out.y = __ddiv_rn(ni, mag);
+    }
+    return x > 0.0; // sqrt(x) > 0 iff x > 0
 }
 
 // |z| as numpy computes it for a contiguous complex128 array on an FMA-capable x86-64

@@ -46,3 +46,28 @@ if which in ("all", "trace"):
             print("utt %d pass %2d: taken %8.3f primed %8.3f computed %8.3f written %8.3f ms; Mclk rows-wait %.2f nbr-poll %.2f work %.2f wait-ctrl %.2f" % (
                 row[0], row[1], row[2] / 1e6, row[3] / 1e6, row[4] / 1e6, row[5] / 1e6, row[6] / 1e6, row[7] / 1e6, row[8] / 1e6, row[9] / 1e6))
     ctx.batch_trace(False)
+if which in ("trace64",):
+    p = lws_b200.lws(1024, 256)
+    x = np.stack([np.random.default_rng(2000 + b).standard_normal(160000) for b in range(64)])
+    A = np.abs(p.stft(x))
+    ctx.batch_trace(True)
+    for cl, sw in ((0, 0), (2, 5), (4, 16)):
+        ctx.set_tuning(0, cl, sw)
+        p.batch_lws(A); p.batch_lws(A)
+        rows = ctx.batch_trace(True)
+        pl = ctx.last_batch_plan()
+        print("plan C=%d G=%d" % (pl["cluster"], pl["sweeps_per_pass"]), ctx.last_compute_ms(), "ms;", len(rows), "items")
+        end = max(r[5] for r in rows)
+        # clusters: items taken in order by the same cluster are those whose 'taken' follows another's 'written'
+        prime = sum(r[3] - r[2] for r in rows) / 1e6
+        comp = sum(r[4] - r[3] for r in rows) / 1e6
+        print("  sum over items: priming %.1f ms, computing %.1f ms; kernel end %.2f ms; mean item %.2f ms" % (prime, comp, end / 1e6, comp / len(rows)))
+        bypass = {}
+        for r in rows:
+            bypass.setdefault(r[1], []).append(r)
+        for ps in sorted(bypass):
+            rs = bypass[ps]
+            print("  pass %2d: items %3d taken %.2f..%.2f  priming mean %.2f max %.2f  computing mean %.2f ms  rows-wait mean %.2f Mclk work %.2f" % (
+                ps, len(rs), min(r[2] for r in rs) / 1e6, max(r[2] for r in rs) / 1e6, np.mean([r[3] - r[2] for r in rs]) / 1e6,
+                max(r[3] - r[2] for r in rs) / 1e6, np.mean([r[4] - r[3] for r in rs]) / 1e6, np.mean([r[6] for r in rs]) / 1e6, np.mean([r[8] for r in rs]) / 1e6))
+    ctx.batch_trace(False); ctx.set_tuning(0, 0, 0)
