@@ -377,7 +377,7 @@ def run_b200_arm(args):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "batch sweep kernel", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_BIN_ITER * bins_rank * it,
-                         "note": "fp64 stencil: the kernel is bounded by the fp64 pipe, not HBM (DESIGN.md)"},
+                         "note": "bit-exact fp64 Gauss-Seidel stencil: bounded by shared-memory bandwidth and in-order fp64 issue of the few warps the ring leaves room for, not by HBM (DESIGN.md section 5)"},
             "cpu_baseline": cpu,
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
             "plan": ctx.last_batch_plan(), "cycles_cluster0": ctx.last_batch_cycles(),

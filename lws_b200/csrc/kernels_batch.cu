@@ -1091,6 +1091,20 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                 } else {
                 int xb = -2 * j;          // block index; negative while the slot has not started
                 int m = j - QS * g;       // frame of the slot
+                // amplitudes of the block (row-major plane in global memory, read-only), fetched one macro-step ahead:
+                // their L2 / HBM latency would otherwise sit in front of every block
+                double ampn[SBK];
+                auto fetch_amp = [&](int xb_, int m_) {
+                    if (has_slot && g < Gp && xb_ >= 0 && xb_ < nb_my && m_ >= 0 && m_ < T) {
+                        const double2 *ap = reinterpret_cast<const double2 *>(v.A + (grow0 + m_ + Q - 1) * P + v.c0 + b0 + SBK * xb_);
+#pragma unroll
+                        for (int q = 0; q < SBK / 2; ++q) {
+                            const double2 a2 = __ldg(ap + q);
+                            ampn[2 * q] = a2.x; ampn[2 * q + 1] = a2.y;
+                        }
+                    }
+                };
+                fetch_amp(xb, m);
                 cta_sync();               // control warp has verified macro-step 0
                 for (int t = 0; t < nsteps; ++t) {
                     const long long k0 = clock64();
@@ -1104,18 +1118,17 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                                 if (!keep_waiting(spins, prm.status, 0x30000000u | (c << 24) | ((pass & 0xff) << 16) | (t & 0xffff))) break;
                         }
                     }
-                    if (has_slot && g < Gp && xb >= 0 && xb < nb_my && m >= 0 && m < T) {
+                    int xb1 = xb + 1, m1 = m; // next macro-step's task of this slot
+                    if (xb1 == NBV) { xb1 = 0; m1 += NS; }
+                    const bool valid = has_slot && g < Gp && xb >= 0 && xb < nb_my && m >= 0 && m < T;
+                    double amp[SBK];
+#pragma unroll
+                    for (int i = 0; i < SBK; ++i) amp[i] = ampn[i];
+                    fetch_amp(xb1, m1);
+                    if (valid) {
                         const int e = m + Q - 1;
                         const int n0 = b0 + SBK * xb;
-                        // amplitudes of the block (row-major plane in global memory, read-only)
-                        const double2 *ap = reinterpret_cast<const double2 *>(v.A + (grow0 + e) * P + v.c0 + n0);
-                        double amp[SBK];
                         unsigned active = 0;
-#pragma unroll
-                        for (int q = 0; q < SBK / 2; ++q) {
-                            const double2 a2 = __ldg(ap + q);
-                            amp[2 * q] = a2.x; amp[2 * q + 1] = a2.y;
-                        }
 #pragma unroll
                         for (int i = 0; i < SBK; ++i)
                             if (n0 + i < Nreal && amp[i] > thr) active |= 1u << i; // lwslib.cpp:295-296
@@ -1139,7 +1152,7 @@ k_batch_strips(const __grid_constant__ StripParams prm, const __grid_constant__ 
                     }
                     const long long k1 = clock64();
                     cta_sync(); // macro-step t done
-                    if (++xb == NBV) { xb = 0; m += NS; }
+                    xb = xb1; m = m1;
                     const long long k2 = clock64();
                     cta_sync(); // neighbours ready for macro-step t + 1
                     tm_work += k1 - k0; tm_waitA += k2 - k1; tm_waitB += clock64() - k2;
