@@ -128,7 +128,7 @@ int lwsb_istft(lwsb_ctx *ctx, const void *S_in, int B, int M, int Nreal, const d
 int lwsb_last_compute_ms(lwsb_ctx *ctx, float *ms);
 long long lwsb_launch_count(const lwsb_ctx *ctx); /* kernels launched by this context so far */
 /* 1 and the plan {cluster size, blocks per strip, virtual blocks, frame slots, sweeps per pass, ring rows,
- * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order, tensor-memory variant} (12 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it
+ * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order, kernel variant, bins per block} (13 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it
  * ran the generic wavefront kernel */
 int lwsb_last_batch_plan(const lwsb_ctx *ctx, int *out9);
 /* tuning knobs of the strip kernel's planner (0 = automatic): shared-memory budget per CTA in bytes, cluster
@@ -141,6 +141,8 @@ int lwsb_set_tuning(lwsb_ctx *ctx, long long smem_limit, int cluster, int sweeps
  * register-window mode (0..2) + 3 * explicit software pipelining (modes other than the default one exist only in
  * builds with -DLWSB_PAIR_EXPERIMENTS and otherwise select the default).  Results do not depend on it. */
 int lwsb_set_variant(lwsb_ctx *ctx, int sweep_lag, int tensor_memory);
+/* bins per block of the strip kernel: 0 = automatic, 8 (frames 2 blocks apart) or 4 (frames 3 blocks apart; Q <= 4).  Also env LWSB_STRIP_BLOCK. */
+int lwsb_set_block_bins(lwsb_ctx *ctx, int bins);
 /* time line of the strip kernel's work items -- one per (utterance, pass); the passes of an utterance run on different
  * clusters at the same time, each a few frames behind the previous one.  enable != 0 switches recording on for the
  * following lwsb_batch calls (also: env LWSB_STRIP_TRACE=1); returns the number of items of the last call copied out:
@@ -166,10 +168,10 @@ int lwsb_get_stats(lwsb_ctx *ctx, double *mean_amp, double *max_amp);
  *    into (row, weight set, rframe, cframe, threshold index or -1). */
 int lwsb_debug_terms(const double *wr, const double *wi, int Q, int L, int fold, int rframe, int cframe, int p,
                      int max_terms, int *dr, int *dk, double *cr, double *ci);
-/*  - lwsb_debug_plan_strips: the plan the cluster strip kernel would use (same 12 numbers as
+/*  - lwsb_debug_plan_strips: the plan the cluster strip kernel would use (same 13 numbers as
  *    lwsb_last_batch_plan) for a shape and a shared-memory / SM budget; returns 0 when the generic kernel serves it. */
 int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, int maxT, int B, long long smem_limit,
-                           int sm_count, int force_cluster, int max_sweeps, int *out9);
+                           int sm_count, int force_cluster, int max_sweeps, int force_block, int *out9);
 long long lwsb_debug_online_chain_length(int T, int iterations, int look_ahead);
 int lwsb_debug_online_task(int T, int iterations, int look_ahead, int Q, long long j, int *row, int *which,
                            int *rframe, int *cframe, int *thr_index);

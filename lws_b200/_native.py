@@ -51,7 +51,8 @@ SIGNATURES = {
     "lwsb_device_info": (_ci, [_vp, _ip, _ip, _ip, ctypes.POINTER(_ll)]),
     "lwsb_get_stats": (_ci, [_vp, _dp, _dp]),
     "lwsb_debug_terms": (_ci, [_dp, _dp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ip, _ip, _dp, _dp]),
-    "lwsb_debug_plan_strips": (_ci, [_ci, _ci, _ci, _ci, _ci, _ci, _ll, _ci, _ci, _ci, _ip]),
+    "lwsb_debug_plan_strips": (_ci, [_ci, _ci, _ci, _ci, _ci, _ci, _ll, _ci, _ci, _ci, _ci, _ip]),
+    "lwsb_set_block_bins": (_ci, [_vp, _ci]),
     "lwsb_set_tuning": (_ci, [_vp, _ll, _ci, _ci]),
     "lwsb_set_variant": (_ci, [_vp, _ci, _ci]),
     "lwsb_last_batch_cycles": (_ci, [_vp, ctypes.POINTER(ctypes.c_ulonglong)]),
@@ -261,6 +262,9 @@ class Context(object):
     def set_tuning(self, smem_limit=0, cluster=0, sweeps_per_pass=0):
         self._c(lib().lwsb_set_tuning(self._h, int(smem_limit), int(cluster), int(sweeps_per_pass)))
 
+    def set_block_bins(self, bins=0):
+        self._c(lib().lwsb_set_block_bins(self._h, int(bins)))
+
     def set_variant(self, sweep_lag=0, tensor_memory=0):
         self._c(lib().lwsb_set_variant(self._h, int(sweep_lag), int(tensor_memory)))
 
@@ -293,7 +297,7 @@ class Context(object):
 
     def last_batch_plan(self):
         """dict describing the cluster strip plan of the last batch() call, or None (generic kernel)."""
-        out = (ctypes.c_int * 12)()
+        out = (ctypes.c_int * 16)()
         if self._c(lib().lwsb_last_batch_plan(self._h, out)) != 1:
             return None
         return dict(zip(PLAN_KEYS, list(out)))
@@ -328,12 +332,12 @@ def debug_terms(Wc, fold, rframe, cframe, p):
 
 
 PLAN_KEYS = ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots", "sweeps_per_pass", "ring_rows",
-             "ring_pitch", "threads", "smem_bytes", "sweep_lag", "sweep_fastest", "tensor_memory")
+             "ring_pitch", "threads", "smem_bytes", "sweep_lag", "sweep_fastest", "tensor_memory", "block_bins")
 
 
-def debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit=232448, sm_count=148, cluster=0, sweeps=0):
-    out = (ctypes.c_int * 12)()
-    if _check(lib().lwsb_debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit, sm_count, cluster, sweeps,
+def debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit=232448, sm_count=148, cluster=0, sweeps=0, block=0):
+    out = (ctypes.c_int * 16)()
+    if _check(lib().lwsb_debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit, sm_count, cluster, sweeps, block,
                                            out)) != 1:
         return None
     return dict(zip(PLAN_KEYS, list(out)))

@@ -77,6 +77,7 @@ struct lwsb_ctx {
     int last_kernel = 0;                   // 0 generic, 1 strips (introspection)
     long long tune_smem = 0;               // tuning knobs (lwsb_set_tuning): shared-memory budget, cluster size,
     int tune_cluster = 0, tune_sweeps = 0; // sweeps per pass; 0 = automatic
+    int tune_block = 0;                    // bins per block of the strip kernel: 0 automatic, 4 or 8 (env LWSB_STRIP_BLOCK, lwsb_set_block_bins)
     int tune_lag = 0;                      // frames between sweeps (env LWSB_STRIP_LAG only)
     int tune_tm = 0;                       // tensor-memory producer/consumer kernel (env LWSB_STRIP_TM=1, lwsb_set_tuning2);
                                            // off by default: measured slower than the single-warp pipeline
@@ -199,6 +200,7 @@ extern "C" int lwsb_create(int device, void *stream, lwsb_ctx **out)
     if (const char *e4 = getenv("LWSB_STRIP_LAG")) c->tune_lag = atoi(e4);
     if (const char *e5 = getenv("LWSB_STRIP_TM")) c->tune_tm = atoi(e5);
     if (const char *e6 = getenv("LWSB_STRIP_TRACE")) c->want_trace = atoi(e6) != 0;
+    if (const char *e7 = getenv("LWSB_STRIP_BLOCK")) c->tune_block = atoi(e7);
     *out = c;
     return LWSB_OK;
 }
@@ -443,7 +445,8 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
                         plan_strips(c->Nreal, c->Q, c->L, active, c->maxT, c->B,
                                     c->tune_smem > 0 ? std::min((size_t)c->tune_smem, c->prop.sharedMemPerBlockOptin)
                                                      : c->prop.sharedMemPerBlockOptin,
-                                    c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps, c->tune_lag, c->tune_tm, fold) &&
+                                    c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps, c->tune_lag, c->tune_tm, fold,
+                                    c->tune_block) &&
                         c->P >= strips_min_pitch(c->Nreal, c->c0);
     if (strips) {
         CU(c, c->status.reserve(256));
@@ -818,6 +821,14 @@ extern "C" int lwsb_set_tuning(lwsb_ctx *c, long long smem_limit, int cluster, i
     return LWSB_OK;
 }
 
+extern "C" int lwsb_set_block_bins(lwsb_ctx *c, int bins)
+{
+    CHECK_CTX(c);
+    if (bins != 0 && bins != 4 && bins != 8) return fail(c, LWSB_ERR_ARG, "bins per block: 0 (automatic), 4 or 8");
+    c->tune_block = bins;
+    return LWSB_OK;
+}
+
 extern "C" int lwsb_set_variant(lwsb_ctx *c, int sweep_lag, int tensor_memory)
 {
     CHECK_CTX(c);
@@ -832,8 +843,8 @@ extern "C" int lwsb_last_batch_plan(const lwsb_ctx *c, int *out9)
     if (!c || !out9) return LWSB_ERR_ARG;
     if (c->last_kernel != 1) return 0;
     const StripPlan &p = c->last_plan;
-    const int v[12] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM};
-    for (int i = 0; i < 12; ++i) out9[i] = v[i];
+    const int v[13] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM, p.SBK};
+    for (int i = 0; i < 13; ++i) out9[i] = v[i];
     return 1;
 }
 
@@ -881,13 +892,13 @@ extern "C" int lwsb_debug_terms(const double *wr, const double *wi, int Q, int L
 }
 
 extern "C" int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, int maxT, int B, long long smem_limit,
-                                      int sm_count, int force_cluster, int max_sweeps, int *out9)
+                                      int sm_count, int force_cluster, int max_sweeps, int force_block, int *out9)
 {
     if (!out9) return LWSB_ERR_ARG;
     StripPlan p;
-    if (!plan_strips(Nreal, Q, L, iterations, maxT, B, (size_t)smem_limit, sm_count, &p, force_cluster, max_sweeps, 0, 0)) return 0;
-    const int v[12] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM};
-    for (int i = 0; i < 12; ++i) out9[i] = v[i];
+    if (!plan_strips(Nreal, Q, L, iterations, maxT, B, (size_t)smem_limit, sm_count, &p, force_cluster, max_sweeps, 0, 0, 0, force_block)) return 0;
+    const int v[13] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM, p.SBK};
+    for (int i = 0; i < 13; ++i) out9[i] = v[i];
     return 1;
 }
 

@@ -16,7 +16,7 @@
 //   * half the registers per value, which makes room for SLIDING WINDOWS: the neighbour frames m-+r are read
 //     from shared memory once per block (18 columns per row) into registers instead of once per use
 //     (59 loads per bin): shared-memory bandwidth, 7.4 clk/bin/SM of traffic before, was the tighter floor.
-#pragma once
+
 
 // ring accessor of one lane: component h of cell (frame + dr, block column + dcol)
 template <int Q>
@@ -230,10 +230,11 @@ __device__ __forceinline__ void pair_block(const PairCell<Q> &cell, PairWin<Q, W
         if (ok) {
             row[2 * col] = val;
             row[2 * mcol] = (mcol != col && h) ? -val : val;
-            if (I < SL && bc.xb == 0 && bc.ring_left)
-                (reinterpret_cast<double *>(bc.ring_left + bc.ownoff) + h)[2 * (SL + SBK * bc.NBr + I)] = val;
-            if (I >= SBK - SL && bc.xb == bc.NBr - 1 && bc.ring_right)
-                (reinterpret_cast<double *>(bc.ring_right + bc.ownoff) + h)[2 * (I - (SBK - SL))] = val;
+            const int q = SBK * bc.xb + I; // bin inside the strip: the first / last L bins also live in a neighbour's halo
+            if (q < SL && bc.ring_left)
+                (reinterpret_cast<double *>(bc.ring_left + bc.ownoff) + h)[2 * (SL + SBK * bc.NBr + q)] = val;
+            if (q >= SBK * bc.NBr - SL && bc.ring_right)
+                (reinterpret_cast<double *>(bc.ring_right + bc.ownoff) + h)[2 * (q - (SBK * bc.NBr - SL))] = val;
         }
         if constexpr (PAT == 1) own.cur[I + 1] = ok ? val : own.cur[I + 1];
         if constexpr (I + 1 < SBK) {

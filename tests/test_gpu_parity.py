@@ -370,3 +370,54 @@ def test_branch_free_sqrt_and_division_match_the_library(gpu):
     chk_s, bad_s, chk_d, bad_d = ctx.debug_fast_math(100_000_000, 7)
     assert chk_s > 90_000_000 and chk_d > 50_000_000, (chk_s, chk_d)  # half the division samples have any exponent: many quotients leave the fast range
     assert bad_s == 0 and bad_d == 0, (bad_s, bad_d)
+
+
+BLOCK4_CASES = [  # fsize, hop, samples, iterations, cluster, sweeps per pass, variant
+    (512, 128, 6000, 6, 1, 0, 0), (512, 128, 6000, 6, 2, 0, 0), (512, 128, 6000, 7, 4, 2, 0), (512, 128, 700, 5, 2, 2, 0),
+    (1024, 256, 30000, 12, 2, 0, 0), (1024, 256, 30000, 12, 4, 0, 0), (1024, 256, 30000, 12, 8, 0, 0), (1024, 256, 30000, 9, 8, 2, 0),
+    (128, 64, 9000, 10, 1, 0, 0), (128, 64, 9000, 10, 2, 3, 0), (512, 128, 32000, 100, 0, 0, 0), (1024, 256, 30000, 12, 4, 0, 11),
+    (512, 128, 9000, 9, 2, 0, 11),
+]
+
+
+@pytest.mark.parametrize("fs,hop,n,its,cluster,sweeps,variant", BLOCK4_CASES, ids=["%d-%d-n%d-it%d-C%d-G%d-V%d" % c for c in BLOCK4_CASES])
+def test_strip_kernel_four_bin_blocks(gpu, oracle, fs, hop, n, its, cluster, sweeps, variant):
+    """4 bins per block, frames 3 blocks apart (the L = 5 halo bins of a strip span two blocks): same bits."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(fs, hop), gpu.lws(fs, hop)
+    A = np.abs(po.stft(make_signal("tonal", 3, n)))
+    try:
+        ctx.set_tuning(0, cluster, sweeps)
+        ctx.set_block_bins(4)
+        ctx.set_variant(0, variant)
+        for thr in (np.zeros(its), gpu.get_thresholds(its, 100 if its > 50 else 2.0, 0.1, 1)):
+            Y = pg.batch_lws(A, thresholds=thr)
+            plan = ctx.last_batch_plan()
+            assert plan is not None and plan["block_bins"] == 4, plan
+            assert cluster == 0 or plan["cluster"] == cluster
+            _close(Y, po.batch_lws(A, thresholds=thr), "4-bin blocks %s" % (plan,))
+    finally:
+        ctx.set_tuning(0, 0, 0)
+        ctx.set_block_bins(0)
+        ctx.set_variant(0, 0)
+
+
+def test_strip_kernel_four_bin_blocks_ragged_batch(gpu, oracle):
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(512, 128), gpu.lws(512, 128)
+    As = [np.abs(po.stft(make_signal("white" if i % 2 else "tonal", 50 + i, 3000 + 700 * (i % 9)))) for i in range(45)]
+    thr = gpu.get_thresholds(9, 2.0, 0.2, 1)
+    want = [po.batch_lws(A, thresholds=thr) for A in As]
+    try:
+        ctx.set_block_bins(4)
+        for cl in (4, 2, 0):
+            ctx.set_tuning(0, cl, 0)
+            Ys = pg.batch_lws(As, thresholds=thr)
+            assert ctx.last_batch_plan()["block_bins"] == 4
+            for i, (Y, W) in enumerate(zip(Ys, want)):
+                _close(Y, W, "ragged member %d, cluster %d, 4-bin blocks" % (i, cl))
+    finally:
+        ctx.set_tuning(0, 0, 0)
+        ctx.set_block_bins(0)

@@ -1,7 +1,7 @@
 """CPU replay of the cluster strip kernel's schedule (lws_b200/csrc/kernels_batch.cu).
 
-The kernel's correctness rests on a dependency argument: blocks of 8 bins, frames 2 blocks
-apart, sweeps Q frames apart, strips NBr macro-steps apart, rows living in a ring of R slots
+The kernel's correctness rests on a dependency argument: blocks of 8 (or 4) bins, frames 2 (or 3)
+blocks apart, sweeps Q frames apart, strips NBr macro-steps apart, rows living in a ring of R slots
 that TMA fills LEAD frames ahead and drains when a frame's last sweep is done, edge blocks
 copied into the neighbour strip's halo.  This test replays exactly that control flow in numpy
 -- per-strip rings with halos, slot reuse, lock-stepped strips, housekeeping at the same
@@ -18,7 +18,7 @@ from conftest import SMALL_CASES, golden, relF
 import lws_b200
 from lws_b200 import _native, dsp
 
-SL, SBK, SLEAD = 5, 8, 2
+SL, SLEAD = 5, 2
 
 
 def _tables(W, fold, Q):
@@ -28,6 +28,7 @@ def _tables(W, fold, Q):
 class Strip(object):
     def __init__(self, c, plan, Nreal):
         self.c = c
+        SBK = plan["block_bins"]
         self.NBr, self.R = plan["blocks_per_strip"], plan["ring_rows"]
         self.b0 = c * self.NBr * SBK
         self.nb_my = min(max((Nreal - self.b0 + SBK - 1) // SBK, 0), self.NBr)
@@ -41,7 +42,9 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
     C, NBr, NBV, NS, G, R = (plan[k] for k in ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots",
                                                 "sweeps_per_pass", "ring_rows"))
     QS = plan["sweep_lag"]
-    assert QS >= Q
+    SBK = plan["block_bins"]
+    LAGB = (SBK + SL + SBK - 1) // SBK   # blocks between consecutive frames: LAGB * SBK >= SBK + L
+    assert QS >= Q and NBV % LAGB == 0 and NS * LAGB == NBV
     Tp = T + 2 * (Q - 1)
     amax = A[Q - 1:Q - 1 + T, SL:SL + Nreal].max()
     act = [i for i, th in enumerate(thr_list) if th * mean < amax]
@@ -49,7 +52,7 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
     assert R >= QS * (G - 1) + 2 * Q + SLEAD + NS
     for ps in range(npass):
         Gp = min(G, len(act) - ps * G)
-        nsteps = 2 * (T - 1 + QS * (Gp - 1)) + NBV
+        nsteps = LAGB * (T - 1 + QS * (Gp - 1)) + NBV
         strips = [Strip(c, plan, Nreal) for c in range(C)]
 
         def load(st, e):
@@ -72,7 +75,7 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
                     continue
                 for g in range(Gp):
                     for j in range(NS):
-                        d = t - 2 * j
+                        d = t - LAGB * j
                         if d < 0:
                             continue
                         xb, m = d % NBV, j + NS * (d // NBV) - QS * g
@@ -109,10 +112,11 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
                                 targets.append((st.c, e % R, SL - n, np.conj(val)))
                             elif Nreal - 1 - SL <= n <= Nreal - 2:
                                 targets.append((st.c, e % R, SL + 2 * (Nreal - 1) - n - st.b0, np.conj(val)))
-                            if xb == 0 and i < SL and st.c > 0:
-                                targets.append((st.c - 1, e % R, SL + SBK * NBr + i, val))
-                            if xb == NBr - 1 and i >= SBK - SL and st.c < C - 1:
-                                targets.append((st.c + 1, e % R, i - (SBK - SL), val))
+                            q = SBK * xb + i   # bin inside the strip: the first / last L bins also live in a neighbour's halo
+                            if q < SL and st.c > 0:
+                                targets.append((st.c - 1, e % R, SL + SBK * NBr + q, val))
+                            if q >= SBK * NBr - SL and st.c < C - 1:
+                                targets.append((st.c + 1, e % R, q - (SBK * NBr - SL), val))
                             for (sc, slot, cc, vv) in targets:
                                 assert strips[sc].tag[slot] == e, "halo write into a slot holding another row"
                                 strips[sc].ring[slot, cc] = vv
@@ -128,22 +132,22 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
                 if not (0 <= t < nsteps):
                     continue
                 tf = t - (st.nb_my - 1)
-                if st.nb_my > 0 and tf >= 0 and tf % 2 == 0:
-                    m = tf // 2 - QS * (Gp - 1)
+                if st.nb_my > 0 and tf >= 0 and tf % LAGB == 0:
+                    m = tf // LAGB - QS * (Gp - 1)
                     if 0 <= m < T:
                         e = m + Q - 1
                         assert st.tag[e % R] == e
                         lo = 0 if st.c == 0 else SL
                         hi = SL + (Nreal - st.b0) + SL if st.c == C - 1 else SL + SBK * NBr
                         E[e, st.b0 + lo:st.b0 + hi] = st.ring[e % R, lo:hi]
-                if (t + 1) % 2 == 0:
-                    e = (t + 1) // 2 + 2 * (Q - 1) + SLEAD
+                if (t + 1) % LAGB == 0:
+                    e = (t + 1) // LAGB + 2 * (Q - 1) + SLEAD
                     if e < Tp:
                         load(st, e)
     return E
 
 
-CASES = [  # (golden case, frames, thresholds, smem budget, cluster, sweeps per pass)
+CASES = [  # (golden case, frames, thresholds, smem budget, cluster, sweeps per pass[, bins per block])
     ("q4", 20, [0.5, 0.2, 0.3, 0.1, 0.05], 232448, 0, 0),          # one strip, all sweeps in one pass
     ("q4", 9, [0.5, 0.2, 0.3, 0.1, 0.05], 232448, 0, 2),           # several passes, a partial last pass
     ("q4b", 24, [0.9, 0.4, 0.2, 0.3], 232448, 2, 0),               # two strips (33 bins: 3 + 2 blocks)
@@ -153,11 +157,23 @@ CASES = [  # (golden case, frames, thresholds, smem budget, cluster, sweeps per 
     ("cfg1_short", 10, [0.8, 0.3, 0.2, 0.25, 0.1, 0.3], 232448, 4, 2),  # 257 bins on 4 strips (9 blocks each, 6 in the last)
     ("rand513", 5, [0.8, 0.3], 232448, 8, 0),                      # 513 bins on 8 strips of 9 blocks (virtual 10)
     ("cfg1_short", 6, [0.8, 0.3, 0.5], 60000, 2, 0),               # a tight ring: small G forced by the budget
+    # 4-bin blocks, frames 3 blocks apart; the L = 5 halo bins span two blocks
+    ("q4", 20, [0.5, 0.2, 0.3, 0.1, 0.05], 232448, 0, 0, 4),
+    ("q4", 9, [0.5, 0.2, 0.3, 0.1, 0.05], 232448, 0, 2, 4),
+    ("q4b", 24, [0.9, 0.4, 0.2, 0.3], 232448, 2, 0, 4),
+    ("q4b", 3, [0.9, 0.4, 0.2], 232448, 2, 2, 4),
+    ("q2", 16, [0.5, 0.25, 0.2, 0.1], 232448, 0, 3, 4),
+    ("cfg1_short", 10, [0.8, 0.3, 0.2, 0.25, 0.1, 0.3], 232448, 4, 2, 4),
+    ("rand513", 5, [0.8, 0.3], 232448, 8, 0, 4),
+    ("rand513", 4, [0.8, 0.3, 0.1], 232448, 4, 2, 4),
+    ("cfg1_short", 6, [0.8, 0.3, 0.5], 60000, 2, 0, 4),
 ]
+CASES = [c if len(c) == 7 else c + (8,) for c in CASES]
 
 
-@pytest.mark.parametrize("name,T,thr,smem,cluster,sweeps", CASES, ids=["%s-T%d-C%d-G%d" % (c[0], c[1], c[4], c[5]) for c in CASES])
-def test_strip_schedule_equals_sequential(oracle, name, T, thr, smem, cluster, sweeps):
+@pytest.mark.parametrize("name,T,thr,smem,cluster,sweeps,block", CASES,
+                         ids=["%s-T%d-C%d-G%d-B%d" % (c[0], c[1], c[4], c[5], c[6]) for c in CASES])
+def test_strip_schedule_equals_sequential(oracle, name, T, thr, smem, cluster, sweeps, block):
     if name == "cfg1_short":
         args, kw = (512, 128), {}
     elif name == "rand513":
@@ -175,8 +191,9 @@ def test_strip_schedule_equals_sequential(oracle, name, T, thr, smem, cluster, s
         A0 = np.abs(golden(name)["X"])[:T]
     T, Nreal = A0.shape
     thr = np.asarray(thr, dtype=np.float64)
-    plan = _native.debug_plan_strips(Nreal, Q, L, len(thr), T, 1, smem_limit=smem, cluster=cluster, sweeps=sweeps)
-    assert plan is not None
+    plan = _native.debug_plan_strips(Nreal, Q, L, len(thr), T, 1, smem_limit=smem, cluster=cluster, sweeps=sweeps, block=block)
+    assert plan is not None and plan["block_bins"] == block
+    SBK = block
     if cluster:
         assert plan["cluster"] == cluster
     fold = {2: 2, 4: 4}.get(Q, 0)
@@ -200,13 +217,16 @@ def test_planner_properties():
         for Q in (2, 4, 8):
             for iters in (1, 7, 100, 200):
                 for smem in (232448, 100000, 30000):
-                    for cluster in (0, 1, 2, 4, 8):
-                        pl = _native.debug_plan_strips(Nreal, Q, 5, iters, 600, 64, smem_limit=smem, cluster=cluster)
+                    for cluster, block in ((0, 0), (1, 0), (2, 0), (4, 0), (8, 0), (0, 4), (2, 4), (4, 4), (8, 4), (0, 8), (4, 8)):
+                        pl = _native.debug_plan_strips(Nreal, Q, 5, iters, 600, 64, smem_limit=smem, cluster=cluster, block=block)
                         if pl is None:
                             continue
+                        SBK = pl["block_bins"]
+                        LAGB = (SBK + SL + SBK - 1) // SBK
+                        assert SBK in (4, 8) and (block == 0 or SBK == block) and SBK % Q == 0 or Q % SBK == 0 and SBK == 8
                         C, NBr, NBV, NS, G, R = (pl[k] for k in ("cluster", "blocks_per_strip", "virtual_blocks",
                                                                  "frame_slots", "sweeps_per_pass", "ring_rows"))
-                        assert NBV % 2 == 0 and NBV >= NBr and NS * 2 == NBV and NBr >= 2
+                        assert NBV % LAGB == 0 and NBV >= NBr and NS * LAGB == NBV and NBr >= 2 and SBK * NBr >= 2 * SL
                         assert C * NBr * SBK >= Nreal                          # the strips cover every bin
                         assert (C - 1) * NBr * SBK <= Nreal - 1 - SL           # mirror zone inside the last strip
                         assert R >= pl["sweep_lag"] * (G - 1) + 2 * Q + SLEAD + NS and 1 <= G <= iters and pl["sweep_lag"] >= Q
