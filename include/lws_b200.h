@@ -122,6 +122,22 @@ int lwsb_stft(lwsb_ctx *ctx, const double *x, int B, int nsamples, const double 
 int lwsb_istft(lwsb_ctx *ctx, const void *S_in, int B, int M, int Nreal, const double *swin, int nswin, int fshift,
                double *x_out, int where);
 
+/* ---- fused calls -----------------------------------------------------
+ * lwsb_reconstruct : waveform -> waveform without leaving the device: y = istft(run_lws(|stft(x)|)) for B signals of
+ *                    equal length (x: (B, nsamples) doubles, y: (B, lwsb_reconstruct_length(...)) doubles, both where
+ *                    `where` says; fftsize = fsize).  The stages are the ones above, chained on the device: the
+ *                    magnitudes are numpy's |.| of the STFT, the windows are host pointers of fsize doubles.
+ *                    consistency_db (host, [B]) is optional: the consistency of the result (below).
+ * lwsb_consistency : get_consistency (lws.pyx:140-144) of B spectrograms (B, M, Nreal) complex128:
+ *                    20 log10(|S| / |stft(istft(S)) - S|), Frobenius norms, one value per spectrogram (host, [B]). */
+long long lwsb_reconstruct_length(int nsamples, int fsize, int fshift, int perfectrec);
+int lwsb_reconstruct(lwsb_ctx *ctx, const double *x, int B, int nsamples, const double *awin, const double *swin, int fsize,
+                     int fshift, int perfectrec, const double *nofuture_thr, int nofuture_it, const double *online_thr,
+                     int online_it, int look_ahead, const double *batch_thr, int batch_it, int flags, double *y_out, int where,
+                     double *consistency_db);
+int lwsb_consistency(lwsb_ctx *ctx, const void *S, int B, int M, int Nreal, const double *awin, const double *swin, int nswin,
+                     int fshift, int perfectrec, int where, double *out_db);
+
 /* ---- introspection used by bench.py / tests -------------------------------------------- */
 /* device time (ms, CUDA events on the context's stream) of the compute kernels of the last
  * lwsb_batch / lwsb_nofuture / lwsb_online call, and how many kernels it launched. */

@@ -45,6 +45,9 @@ SIGNATURES = {
         "lwsb_stft_prepad": (_ci, [_ci, _ci, _ci]),
     "lwsb_stft": (_ci, [_vp, _vp, _ci, _ci, _dp, _ci, _ci, _ci, _ci, _ci, _vp, _ci]),
     "lwsb_istft": (_ci, [_vp, _vp, _ci, _ci, _ci, _dp, _ci, _ci, _vp, _ci]),
+    "lwsb_reconstruct_length": (_ll, [_ci, _ci, _ci, _ci]),
+    "lwsb_reconstruct": (_ci, [_vp, _vp, _ci, _ci, _dp, _dp, _ci, _ci, _ci, _dp, _ci, _dp, _ci, _ci, _dp, _ci, _ci, _vp, _ci, _dp]),
+    "lwsb_consistency": (_ci, [_vp, _vp, _ci, _ci, _ci, _dp, _dp, _ci, _ci, _ci, _ci, _dp]),
     "lwsb_last_compute_ms": (_ci, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "lwsb_launch_count": (_ll, [_vp]),
     "lwsb_last_batch_plan": (_ci, [_vp, _ip]),
@@ -251,6 +254,35 @@ class Context(object):
         out = np.empty((B, fshift * (M - 1) + 2 * (Nreal - 1)))
         self._c(lib().lwsb_istft(self._h, S.ctypes.data, B, M, Nreal, _dptr(swin), len(swin), fshift,
                                  out.ctypes.data, HOST))
+        return out
+
+    def reconstruct(self, x, awin, swin, fsize, fshift, perfectrec, nf_thr, on_thr, look_ahead, ba_thr, flags=0,
+                    consistency=False):
+        """x: (B, nsamples) float64 -> y = istft(run_lws(|stft(x)|)), (B, n_out) float64, in one call on the device
+        (the three weight sets must have been set); with `consistency`, also the consistency in dB of each result."""
+        B, n = x.shape
+        pr = int(bool(perfectrec))
+        ylen = _check(lib().lwsb_reconstruct_length(n, fsize, fshift, pr))
+        y = np.empty((B, ylen))
+        awin = np.ascontiguousarray(awin, dtype=np.float64)
+        swin = np.ascontiguousarray(swin, dtype=np.float64)
+        thr = [np.ascontiguousarray(t, dtype=np.float64) for t in (nf_thr, on_thr, ba_thr)]
+        cons = np.empty(B) if consistency else None
+        # keep a 1-element buffer alive for empty threshold lists (the pointer is not read when the count is 0)
+        ptr = [_dptr(t) if len(t) else _dptr(np.zeros(1)) for t in thr]
+        self._c(lib().lwsb_reconstruct(self._h, x.ctypes.data, B, n, _dptr(awin), _dptr(swin), fsize, fshift, pr,
+                                       ptr[0], len(thr[0]), ptr[1], len(thr[1]), int(look_ahead), ptr[2], len(thr[2]), int(flags),
+                                       y.ctypes.data, HOST, _dptr(cons) if consistency else None))
+        return (y, cons) if consistency else y
+
+    def consistency(self, S, awin, swin, fshift, perfectrec):
+        """S: (B, M, Nreal) complex128 -> (B,) consistency in dB (lws.pyx:140-144), computed on the device."""
+        B, M, Nreal = S.shape
+        awin = np.ascontiguousarray(awin, dtype=np.float64)
+        swin = np.ascontiguousarray(swin, dtype=np.float64)
+        out = np.empty(B)
+        self._c(lib().lwsb_consistency(self._h, S.ctypes.data, B, M, Nreal, _dptr(awin), _dptr(swin), len(swin), fshift,
+                                       int(bool(perfectrec)), HOST, _dptr(out)))
         return out
 
     # -- introspection ----------------------------------------------------------------------

@@ -281,6 +281,32 @@ class lws(object):
                   'The current code uses simplifications that rely on such symmetry, so the code may not behave properly.')
 
     # ---- transforms (GPU) -------------------------------------------------------------------
+    def reconstruct(self, x, *, return_consistency=False):
+        """Waveform -> waveform on the device (an extension; the reference chains four calls through the host):
+        ``istft(run_lws(abs(stft(x))))`` for a signal or a (B, nsamples) batch of equal-length signals, with the class's
+        iteration settings.  With ``return_consistency`` also the consistency (dB) of the reconstructed spectrogram(s)."""
+        x = np.asarray(x)
+        batched = x.ndim == 2
+        if x.ndim not in (1, 2):
+            raise ValueError('We only deal with single channel signals here')
+        if np.iscomplexobj(x):
+            raise TypeError('real signals only')
+        _check_weights(self.W, self.use_simplifications)
+        nf = get_thresholds(self.nofuture_iterations, self.nofuture_alpha, self.nofuture_beta, self.nofuture_gamma)
+        on = get_thresholds(self.online_iterations, self.online_alpha, self.online_beta, self.online_gamma)
+        ba = get_thresholds(self.batch_iterations, self.batch_alpha, self.batch_beta, self.batch_gamma)
+        xb = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        ctx = _context(_devices(self.device)[0])
+        ctx.set_weights(_native.W, self.W)
+        ctx.set_weights(_native.W_AI, self.W_ai)
+        ctx.set_weights(_native.W_AF, self.W_af)
+        res = ctx.reconstruct(xb, self.awin, self.swin, int(self.fsize), int(self.fshift), self.perfectrec is True, nf, on,
+                              self.look_ahead, ba, consistency=return_consistency)
+        if return_consistency:
+            y, c = res
+            return (y, c) if batched else (y[0], float(c[0]))
+        return res if batched else res[0]
+
     def get_consistency(self, S):
         from . import transforms
         return transforms.get_consistency(S, self.fsize, self.fshift, self.awin, self.swin,

@@ -69,6 +69,7 @@ struct lwsb_ctx {
     std::vector<int> stat_tabs;                         // host copy of the summation trees, concatenated
     std::map<long long, std::pair<int, int>> stat_index; // array length -> (first leaf, leaf count)
     DevBuf fx, fS, fwin, fframes;          // stft / istft staging
+    DevBuf rx, rS, rR, ry, rn;             // fused waveform -> waveform call and consistency: signals, spectrograms, norms
     DevBuf status;                         // watchdog word of the strip kernel
     DevBuf items, done, trace;             // strip kernel: (utterance, pass) work list, per-strip progress counters, optional time stamps
     bool want_trace = false;               // env LWSB_STRIP_TRACE=1 / lwsb_last_batch_trace
@@ -210,7 +211,7 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
     CHECK_CTX(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->items, &c->done, &c->trace, &c->E, &c->A, &c->row_max, &c->leaf_tab, &c->tab_of, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
+    for (DevBuf *b : {&c->rx, &c->rS, &c->rR, &c->ry, &c->rn, &c->items, &c->done, &c->trace, &c->E, &c->A, &c->row_max, &c->leaf_tab, &c->tab_of, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
                       &c->drowbase, &c->stage, &c->dptr, &c->dthr, &c->flags, &c->fx, &c->fS, &c->fwin, &c->fframes, &c->status})
         b->release();
     for (auto &kv : c->twiddles) kv.second.release();
@@ -755,6 +756,131 @@ extern "C" int lwsb_istft(lwsb_ctx *c, const void *S_in, int B, int M, int Nreal
     CU(c, launch_istft(dS, B, M, N, logN, c->fwin.as<double>(), nswin, fshift, tw, c->fframes.as<double>(), dx, c->stream));
     c->launches += 2;
     if (where == LWSB_HOST) CU(c, cudaMemcpyAsync(x_out, dx, (size_t)B * len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LWSB_OK;
+}
+
+// ============================================================================ fused calls
+namespace {
+
+// length of the signal istft returns for M frames (transforms.istft: the perfect-reconstruction slice of lws.pyx:135)
+long long istft_length(int M, int fsize, int fshift, int perfectrec, int *crop_lo)
+{
+    const long long full = (long long)fshift * (M - 1) + fsize;
+    *crop_lo = 0;
+    if (!perfectrec) return full;
+    *crop_lo = lwsb_stft_prepad(fsize, fshift, 1);
+    if (fsize == fshift) return 0; // sig[:, pre:0] is empty
+    return std::max(0LL, full - *crop_lo - (fsize - fshift));
+}
+
+// consistency of the B spectrograms at dS (device, (B, M, Nreal) complex128): 20 log10(|S| / |stft(istft(S)) - S|)
+int consistency_device(lwsb_ctx *c, const double2 *dS, int B, int M, int Nreal, const double *awin, const double *swin, int nswin,
+                       int fsize, int fshift, int perfectrec, double *out_db)
+{
+    int lo = 0;
+    const long long ylen = istft_length(M, fsize, fshift, perfectrec, &lo);
+    const long long full = (long long)fshift * (M - 1) + fsize;
+    if (ylen <= 0 || lwsb_stft_frames((int)ylen, fsize, fshift, perfectrec) != M)
+        return fail(c, LWSB_ERR_UNSUPPORTED, "consistency: stft(istft(S)) does not have the shape of S for these parameters");
+    CU(c, c->ry.reserve((size_t)B * full * sizeof(double)));
+    if (int r = lwsb_istft(c, dS, B, M, Nreal, swin, nswin, fshift, c->ry.as<double>(), LWSB_DEVICE)) return r;
+    CU(c, c->rx.reserve((size_t)B * ylen * sizeof(double)));
+    CU(c, cudaMemcpy2DAsync(c->rx.p, (size_t)ylen * sizeof(double), c->ry.as<double>() + lo, (size_t)full * sizeof(double),
+                            (size_t)ylen * sizeof(double), B, cudaMemcpyDeviceToDevice, c->stream));
+    const size_t nS = (size_t)B * M * Nreal;
+    CU(c, c->rR.reserve(nS * sizeof(double2)));
+    if (int r = lwsb_stft(c, c->rx.as<double>(), B, (int)ylen, awin, fsize, fshift, fsize, lwsb_stft_prepad(fsize, fshift, perfectrec), M,
+                          c->rR.p, LWSB_DEVICE))
+        return r;
+    const int nblk = 64;
+    CU(c, c->rn.reserve(((size_t)B * nblk * 2 + (size_t)B * 2) * sizeof(double)));
+    double *partial = c->rn.as<double>(), *sums = partial + (size_t)B * nblk * 2;
+    CU(c, launch_sq_norms(dS, c->rR.as<double2>(), B, (long long)M * Nreal, partial, nblk, sums, c->stream));
+    c->launches += 2;
+    std::vector<double> h(2 * (size_t)B);
+    CU(c, cudaMemcpyAsync(h.data(), sums, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < B; ++b) out_db[b] = 20.0 * std::log10(std::sqrt(h[2 * b]) / std::sqrt(h[2 * b + 1]));
+    return LWSB_OK;
+}
+
+} // namespace
+
+extern "C" long long lwsb_reconstruct_length(int nsamples, int fsize, int fshift, int perfectrec)
+{
+    const int M = lwsb_stft_frames(nsamples, fsize, fshift, perfectrec);
+    if (M < 1) return LWSB_ERR_ARG;
+    int lo;
+    return istft_length(M, fsize, fshift, perfectrec, &lo);
+}
+
+extern "C" int lwsb_consistency(lwsb_ctx *c, const void *S, int B, int M, int Nreal, const double *awin, const double *swin,
+                                int nswin, int fshift, int perfectrec, int where, double *out_db)
+{
+    CHECK_CTX(c);
+    if (!S || !awin || !swin || !out_db || B < 1 || M < 1 || Nreal < 2 || nswin < 1 || fshift < 1 ||
+        (where != LWSB_HOST && where != LWSB_DEVICE))
+        return fail(c, LWSB_ERR_ARG, "bad lwsb_consistency arguments");
+    if (Nreal % 2 != 1) return fail(c, LWSB_ERR_EVEN_NREAL, "We expect the spectrogram to only have non-negative frequencies");
+    if (int r = use_device(c)) return r;
+    const int fsize = 2 * (Nreal - 1);
+    const double2 *dS = reinterpret_cast<const double2 *>(S);
+    if (where == LWSB_HOST) {
+        const size_t nS = (size_t)B * M * Nreal;
+        CU(c, c->rS.reserve(nS * sizeof(double2)));
+        CU(c, cudaMemcpyAsync(c->rS.p, S, nS * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+        dS = c->rS.as<double2>();
+    }
+    return consistency_device(c, dS, B, M, Nreal, awin, swin, nswin, fsize, fshift, perfectrec, out_db);
+}
+
+// y = istft(run_lws(|stft(x)|)) for B signals of equal length without leaving the device (lws.pyx:43-137, 495-499 chained)
+extern "C" int lwsb_reconstruct(lwsb_ctx *c, const double *x, int B, int nsamples, const double *awin, const double *swin,
+                                int fsize, int fshift, int perfectrec, const double *nofuture_thr, int nofuture_it,
+                                const double *online_thr, int online_it, int look_ahead, const double *batch_thr, int batch_it,
+                                int flags, double *y_out, int where, double *consistency_db)
+{
+    CHECK_CTX(c);
+    if (!x || !awin || !swin || !y_out || B < 1 || nsamples < 1 || fsize < 2 || fsize % 2 || fshift < 1 ||
+        (where != LWSB_HOST && where != LWSB_DEVICE))
+        return fail(c, LWSB_ERR_ARG, "bad lwsb_reconstruct arguments");
+    if (int r = use_device(c)) return r;
+    const int M = lwsb_stft_frames(nsamples, fsize, fshift, perfectrec), Nreal = fsize / 2 + 1;
+    if (M < 1) return fail(c, LWSB_ERR_ARG, "signal too short for one frame");
+    int lo = 0;
+    const long long ylen = istft_length(M, fsize, fshift, perfectrec, &lo);
+    const long long full = (long long)fshift * (M - 1) + fsize;
+    const double *dx = x;
+    if (where == LWSB_HOST) {
+        CU(c, c->rx.reserve((size_t)B * nsamples * sizeof(double)));
+        CU(c, cudaMemcpyAsync(c->rx.p, x, (size_t)B * nsamples * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        dx = c->rx.as<double>();
+    }
+    const size_t per = (size_t)M * Nreal;
+    CU(c, c->rS.reserve((size_t)B * per * sizeof(double2)));
+    if (int r = lwsb_stft(c, dx, B, nsamples, awin, fsize, fshift, fsize, lwsb_stft_prepad(fsize, fshift, perfectrec), M, c->rS.p, LWSB_DEVICE))
+        return r;
+    // the magnitudes np.abs(stft(x)) a caller of the reference hands to run_lws (the phases are discarded)
+    CU(c, c->rR.reserve((size_t)B * per * sizeof(double)));
+    CU(c, launch_cabs(c->rS.as<double2>(), c->rR.as<double>(), (long long)B * per, c->stream));
+    c->launches += 1;
+    std::vector<const void *> in(B);
+    std::vector<void *> out(B);
+    std::vector<int> T(B, M);
+    for (int b = 0; b < B; ++b) { in[b] = c->rR.as<double>() + b * per; out[b] = c->rS.as<double2>() + b * per; }
+    if (int r = lwsb_run_lws(c, in.data(), out.data(), T.data(), B, Nreal, LWSB_F64, LWSB_DEVICE, nofuture_thr, nofuture_it, online_thr,
+                             online_it, look_ahead, batch_thr, batch_it, flags))
+        return r;
+    if (consistency_db)
+        if (int r = consistency_device(c, c->rS.as<double2>(), B, M, Nreal, awin, swin, fsize, fsize, fshift, perfectrec, consistency_db))
+            return r;
+    CU(c, c->ry.reserve((size_t)B * full * sizeof(double)));
+    if (int r = lwsb_istft(c, c->rS.p, B, M, Nreal, swin, fsize, fshift, c->ry.as<double>(), LWSB_DEVICE)) return r;
+    if (ylen > 0)
+        CU(c, cudaMemcpy2DAsync(y_out, (size_t)ylen * sizeof(double), c->ry.as<double>() + lo, (size_t)full * sizeof(double),
+                                (size_t)ylen * sizeof(double), B, where == LWSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return LWSB_OK;
 }

@@ -55,6 +55,9 @@ cudaError_t launch_stft(const double *x, int B, int nsamples, const double *awin
                         int pre, const double2 *tw, double2 *S, int M, cudaStream_t s);
 cudaError_t launch_istft(const double2 *S, int B, int M, int N, int logN, const double *swin, int nswin, int hop,
                          const double2 *tw, double *frames, double *signal, cudaStream_t s);
+cudaError_t launch_cabs(const double2 *S, double *A, long long n, cudaStream_t s);
+cudaError_t launch_sq_norms(const double2 *S, const double2 *R, int B, long long n, double *partial, int nblk, double *out,
+                            cudaStream_t s);
 inline int online_generic_max_nreal(int L) { return (1024 - 1) * (L + 1); }
 
 } // namespace lwsb

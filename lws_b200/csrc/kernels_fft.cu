@@ -8,6 +8,8 @@
 // (Hermitian extension, lws.pyx:121-122) and a gather-form overlap-add that sums the frames
 // in increasing frame order like the reference's `signal[...] += ...` loop (lws.pyx:126).
 #include <cuda_runtime.h>
+#include <algorithm>
+#include "exact.cuh"
 #include "kernels.h"
 
 namespace lwsb {
@@ -152,6 +154,65 @@ cudaError_t launch_istft(const double2 *S, int B, int M, int N, int logN, const 
     k_istft_frames<<<dim3(M, B), 256, sm, s>>>(S, swin, nswin, N, logN, tw, frames, M);
     const long long len = (long long)hop * (M - 1) + N;
     k_overlap_add<<<dim3((unsigned)((len + 255) / 256), B), 256, 0, s>>>(frames, N, hop, M, signal, len);
+    return cudaGetLastError();
+}
+
+// Per-utterance squared norms for get_consistency (lws.pyx:140-144): out[2b] = sum |S|^2, out[2b+1] = sum |R - S|^2.
+// One partial sum per block (fixed tree), added in block order by a second tiny kernel: the result does not depend
+// on the order in which blocks finish.
+__global__ void k_sq_norms(const double2 *S, const double2 *R, long long n, double *partial, int nblk)
+{
+    __shared__ double sa[256], sb[256];
+    const int b = blockIdx.y;
+    const double2 *s = S + (long long)b * n, *r = R + (long long)b * n;
+    double a = 0.0, d = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 x = s[i], y = r[i];
+        a += x.x * x.x + x.y * x.y;
+        const double ex = y.x - x.x, ey = y.y - x.y;
+        d += ex * ex + ey * ey;
+    }
+    sa[threadIdx.x] = a; sb[threadIdx.x] = d;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { sa[threadIdx.x] += sa[threadIdx.x + w]; sb[threadIdx.x] += sb[threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[((long long)b * nblk + blockIdx.x) * 2] = sa[0];
+        partial[((long long)b * nblk + blockIdx.x) * 2 + 1] = sb[0];
+    }
+}
+__global__ void k_sq_norms_finish(const double *partial, int nblk, double *out)
+{
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        double a = 0.0, d = 0.0;
+        for (int i = 0; i < nblk; ++i) { a += partial[((long long)b * nblk + i) * 2]; d += partial[((long long)b * nblk + i) * 2 + 1]; }
+        out[2 * b] = a; out[2 * b + 1] = d;
+    }
+}
+
+// |S| as numpy computes it (np.abs of a complex128 array: x_cabs) -- the magnitudes a caller of the reference would
+// hand to run_lws
+__global__ void k_cabs(const double2 *S, double *A, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 z = S[i];
+        A[i] = x_cabs(z.x, z.y);
+    }
+}
+cudaError_t launch_cabs(const double2 *S, double *A, long long n, cudaStream_t s)
+{
+    k_cabs<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, s>>>(S, A, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sq_norms(const double2 *S, const double2 *R, int B, long long n, double *partial, int nblk, double *out,
+                            cudaStream_t s)
+{
+    k_sq_norms<<<dim3(nblk, B), 256, 0, s>>>(S, R, n, partial, nblk);
+    k_sq_norms_finish<<<B, 32, 0, s>>>(partial, nblk, out);
     return cudaGetLastError();
 }
 

@@ -64,8 +64,19 @@ def istft(spec, fshift, swin, awin=None, fftsize=None, perfectrec=False, *, devi
 
 
 def get_consistency(S, fsize, fshift, awin, swin, perfectrec=False, *, device=None):
-    """Consistency in dB (lws.pyx:140-144): 20 log10(|S| / |stft(istft(S)) - S|)."""
+    """Consistency in dB (lws.pyx:140-144): 20 log10(|S| / |stft(istft(S)) - S|), computed on the device in one call
+    (istft, stft and the two Frobenius norms; the spectrogram crosses PCIe once).  A 3-D S gives one value per
+    spectrogram."""
     S = np.asarray(S)
-    tmp = stft(istft(S, fshift, swin, perfectrec=perfectrec, device=device), fsize, fshift, awin,
-               perfectrec=perfectrec, device=device)
-    return 20 * np.log10(np.linalg.norm(S) / np.linalg.norm(tmp - S))
+    batched = S.ndim == 3
+    if S.ndim not in (2, 3):
+        raise ValueError('We only deal with single channel signals here')
+    if S.shape[-1] % 2 != 1:
+        raise ValueError('We expect the spectrogram to only have non-negative frequencies')
+    if 2 * (S.shape[-1] - 1) != fsize:
+        raise NotImplementedError('get_consistency with fftsize != fsize is not supported by the CUDA implementation')
+    awin = np.squeeze(np.asarray(awin, dtype=np.float64))
+    swin = np.squeeze(np.asarray(swin, dtype=np.float64))
+    Sb = np.ascontiguousarray(S if batched else S[None], dtype=np.complex128)
+    c = _ctx(device).consistency(Sb, awin, swin, int(fshift), perfectrec is True)
+    return c if batched else float(c[0])

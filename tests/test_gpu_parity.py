@@ -421,3 +421,44 @@ def test_strip_kernel_four_bin_blocks_ragged_batch(gpu, oracle):
     finally:
         ctx.set_tuning(0, 0, 0)
         ctx.set_block_bins(0)
+
+
+# ------------------------------------------------------------------ fused calls
+@pytest.mark.parametrize("fs,hop,mode,perfectrec", [(512, 128, "music", True), (512, 128, "speech", True), (256, 64, "music", False),
+                                                     (128, 64, "music", True)])
+def test_reconstruct_equals_the_chained_calls(gpu, oracle, fs, hop, mode, perfectrec):
+    """lwsb_reconstruct (waveform -> waveform on the device) against the chain stft -> abs -> run_lws -> istft: bit-identical
+    to the four separate calls of this library (same kernels, same intermediate values), and -- where the iteration does
+    not amplify the 1e-16 difference between the two FFTs (no NoFuture_LWSQ4 stage) -- equal to the
+    oracle's chain to round-off."""
+    kw = dict(mode=mode, perfectrec=perfectrec, batch_iterations=12)
+    po, pg = oracle.lws(fs, hop, **kw), gpu.lws(fs, hop, **kw)
+    x = np.stack([make_signal("tonal", 21, 6000), make_signal("white", 22, 6000)])
+    y, cons = pg.reconstruct(x, return_consistency=True)
+    Yg = pg.run_lws(np.abs(pg.stft(x)))
+    yg = pg.istft(Yg)
+    assert y.shape == yg.shape and np.array_equal(y, yg)
+    for b in range(2):
+        assert abs(cons[b] - pg.get_consistency(Yg[b])) < 1e-9
+        assert po.istft(po.stft(x[b])).shape == y[b].shape
+    if mode == "speech":  # batch sweeps only
+        for b in range(2):
+            want = po.istft(po.run_lws(np.abs(po.stft(x[b]))))
+            assert np.abs(y[b] - want).max() <= 1e-8 * max(1.0, np.abs(want).max())
+    y1 = pg.reconstruct(x[0])
+    assert y1.shape == y[0].shape and np.array_equal(y1, y[0])
+
+
+def test_consistency_on_device(gpu, oracle):
+    po, pg = oracle.lws(512, 128), gpu.lws(512, 128)
+    x = make_signal("tonal", 5, 8000)
+    X = po.stft(x)
+    rng = np.random.default_rng(3)
+    S = np.abs(X) * np.exp(1j * rng.uniform(-np.pi, np.pi, X.shape))
+    for Z in (S, po.batch_lws(np.abs(X), iterations=5)):
+        assert abs(pg.get_consistency(Z) - po.get_consistency(Z)) < 1e-8
+    # a true STFT is consistent to round-off: both sides report ~300 dB, compare loosely
+    assert pg.get_consistency(X) > 250 and po.get_consistency(X) > 250
+    from lws_b200 import transforms
+    both = transforms.get_consistency(np.stack([S, S[::-1]]), 512, 128, pg.awin, pg.swin, perfectrec=True)
+    assert both.shape == (2,) and abs(both[0] - po.get_consistency(S)) < 1e-8
