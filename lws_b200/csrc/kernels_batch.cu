@@ -43,6 +43,7 @@ namespace {
 constexpr int SL = 5;          // stencil reach in bins this kernel is specialised for (L)
 constexpr int SBK_MAX = 8;     // bins per block: 8 or 4 (namespaces bk8 / bk4 below)
 constexpr int SLEAD = 2;       // frames of TMA look-ahead
+constexpr int PUBLISH_EVERY = 4; // a pass publishes its progress to the next pass of the utterance every so many frames
 constexpr unsigned SPIN_LIMIT = 1u << 24; // polls before a wait is declared dead (seconds)
 constexpr unsigned PASS_SPIN_LIMIT = 1u << 27; // waits for another cluster's pass: it may still be busy with earlier work items
 #ifdef LWSB_PAIR_EXPERIMENTS
@@ -317,7 +318,7 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                                                  (C > 2 ? 2000.0 : 0.0) + (C > 4 ? 1500.0 : 0.0);
                 // throughput bound, and the critical path of one utterance: its passes run concurrently on different
                 // clusters, each `lag` macro-steps behind the previous one (it reads what that one has written back)
-                const double lag = (double)LAGB * (Q + SLEAD + QS * (G - 1)) + NBV + LAGB + (C - 1) * NBr;
+                const double lag = (double)LAGB * (Q + SLEAD + QS * (G - 1) + PUBLISH_EVERY) + NBV + LAGB + (C - 1) * NBr;
                 const double cost = std::max(std::ceil((double)B * npass / ncl) * (steps * t_step + 60000.0),
                                              (steps + (npass - 1) * lag) * t_step + 60000.0);
                 if (!found || cost < best) {

@@ -51,7 +51,7 @@ if which in ("trace64",):
     x = np.stack([np.random.default_rng(2000 + b).standard_normal(160000) for b in range(64)])
     A = np.abs(p.stft(x))
     ctx.batch_trace(True)
-    for cl, sw in ((0, 0), (2, 5), (4, 16)):
+    for cl, sw in ((0, 0),):
         ctx.set_tuning(0, cl, sw)
         p.batch_lws(A); p.batch_lws(A)
         rows = ctx.batch_trace(True)
@@ -67,7 +67,8 @@ if which in ("trace64",):
             bypass.setdefault(r[1], []).append(r)
         for ps in sorted(bypass):
             rs = bypass[ps]
-            print("  pass %2d: items %3d taken %.2f..%.2f  priming mean %.2f max %.2f  computing mean %.2f ms  rows-wait mean %.2f Mclk work %.2f" % (
+            print("  pass %2d: items %3d taken %.2f..%.2f  priming mean %.2f max %.2f  computing mean %.2f ms  Mclk: rows-wait %.2f nbr-poll %.2f work %.2f wait-ctrl %.2f" % (
                 ps, len(rs), min(r[2] for r in rs) / 1e6, max(r[2] for r in rs) / 1e6, np.mean([r[3] - r[2] for r in rs]) / 1e6,
-                max(r[3] - r[2] for r in rs) / 1e6, np.mean([r[4] - r[3] for r in rs]) / 1e6, np.mean([r[6] for r in rs]) / 1e6, np.mean([r[8] for r in rs]) / 1e6))
+                max(r[3] - r[2] for r in rs) / 1e6, np.mean([r[4] - r[3] for r in rs]) / 1e6, np.mean([r[6] for r in rs]) / 1e6,
+                np.mean([r[7] for r in rs]) / 1e6, np.mean([r[8] for r in rs]) / 1e6, np.mean([r[9] for r in rs]) / 1e6))
     ctx.batch_trace(False); ctx.set_tuning(0, 0, 0)
