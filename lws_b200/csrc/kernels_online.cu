@@ -115,6 +115,219 @@ __device__ __forceinline__ void online_weighted_sum(const OnlineRingCell &E, con
     }
 }
 
+// ---------------------------------------------------------------- two bins per step (Q <= 4)
+// The same rule split in two: the values of the inter-frame terms (frames m -+ r, r >= 1: they do not depend on the bin
+// updated just before) and the order-bound part (centre-frame terms, the sum in the reference's order, projection).
+// A task takes two consecutive bins per step: the term values of both are formed first -- independent work that
+// overlaps -- then the two chains run one after the other.  Half the CTA barriers per bin as well.
+template <int Q, int FOLD>
+struct OnlineVals {
+    static constexpr int PER_R = FOLD == LWSB_FOLD_ANY ? 1 + 2 * OL : 1 + OL;
+    static constexpr int N = (Q - 1) * PER_R;
+    double r[N > 0 ? N : 1], i[N > 0 ? N : 1];
+};
+
+__device__ __forceinline__ void online_value(double ar, double ai, double br, double bi, double cr, double ci, double &vr, double &vi)
+{
+    vr = __dsub_rn(__dmul_rn(ar, __dadd_rn(br, cr)), __dmul_rn(ai, __dsub_rn(bi, ci)));
+    vi = __dadd_rn(__dmul_rn(ar, __dadd_rn(bi, ci)), __dmul_rn(ai, __dsub_rn(br, cr)));
+}
+
+// the frame pairs in the order the reference adds them: odd bins of the Q4 folding take r = 1, 3 (sign-flipped) then 2
+template <int Q, int P, int FOLD, class F>
+__device__ __forceinline__ void online_for_each_pair(F &&f)
+{
+    using T_ = std::true_type;
+    using F_ = std::false_type;
+    constexpr int PER_R = OnlineVals<Q, FOLD>::PER_R;
+    if constexpr (FOLD == LWSB_FOLD_Q4 && (P & 1)) {
+        f(std::integral_constant<int, 1>{}, T_{}, std::integral_constant<int, 0>{});
+        f(std::integral_constant<int, 3>{}, T_{}, std::integral_constant<int, PER_R>{});
+        f(std::integral_constant<int, 2>{}, F_{}, std::integral_constant<int, 2 * PER_R>{});
+    } else {
+        if constexpr (Q > 1) f(std::integral_constant<int, 1>{}, F_{}, std::integral_constant<int, 0>{});
+        if constexpr (Q > 2) f(std::integral_constant<int, 2>{}, F_{}, std::integral_constant<int, PER_R>{});
+        if constexpr (Q > 3) f(std::integral_constant<int, 3>{}, F_{}, std::integral_constant<int, 2 * PER_R>{});
+    }
+}
+
+template <int Q, int P, int FOLD>
+__device__ __forceinline__ void online_values(const OnlineRingCell &E, const OnlineW<Q> &w, int ws, int rframe, OnlineVals<Q, FOLD> &v)
+{
+    constexpr int PN = (Q - P) % Q;
+    const double2 zero = make_double2(0.0, 0.0);
+    online_for_each_pair<Q, P, FOLD>([&](auto rc, auto minusc, auto basec) {
+        constexpr int r = decltype(rc)::value;
+        constexpr bool minus = decltype(minusc)::value;
+        constexpr int base = decltype(basec)::value;
+        const bool both = r < rframe;
+        {
+            const double2 b = E(-r, 0), c0 = E(+r, 0);
+            const double2 c = both ? c0 : zero;
+            online_value(w.wr[ws][P][r][0], w.wi[ws][P][r][0], b.x, b.y, c.x, c.y, v.r[base], v.i[base]);
+        }
+#pragma unroll
+        for (int k = 1; k <= OL; ++k) {
+            const double2 e1 = E(-r, -k), e4 = E(-r, +k), e2l = E(+r, +k), e3l = E(+r, -k);
+            const double2 e2 = both ? e2l : zero, e3 = both ? e3l : zero;
+            if (FOLD == LWSB_FOLD_ANY) {
+                online_value(w.wr[ws][P][r][k], w.wi[ws][P][r][k], e1.x, e1.y, e3.x, e3.y, v.r[base + 2 * k - 1], v.i[base + 2 * k - 1]);
+                online_value(w.wr[ws][PN][r][k], w.wi[ws][PN][r][k], e2.x, e2.y, e4.x, e4.y, v.r[base + 2 * k], v.i[base + 2 * k]);
+            } else {
+                double br, bi, cr, ci;
+                if (minus) {
+                    br = __dsub_rn(e1.x, e2.x); bi = __dsub_rn(e1.y, e2.y);
+                    cr = __dsub_rn(e3.x, e4.x); ci = __dsub_rn(e3.y, e4.y);
+                } else {
+                    br = __dadd_rn(e1.x, e2.x); bi = __dadd_rn(e1.y, e2.y);
+                    cr = __dadd_rn(e3.x, e4.x); ci = __dadd_rn(e3.y, e4.y);
+                }
+                online_value(w.wr[ws][P][r][k], w.wi[ws][P][r][k], br, bi, cr, ci, v.r[base + k], v.i[base + k]);
+            }
+        }
+    });
+}
+
+// centre-frame terms (they see the bin updated just before), then the term values in the reference's order
+template <int Q, int P, int FOLD>
+__device__ __forceinline__ void online_accumulate(const OnlineRingCell &E, const OnlineW<Q> &w, int ws, int cframe,
+                                                  const OnlineVals<Q, FOLD> &v, double &tr, double &ti)
+{
+    constexpr int PN = (Q - P) % Q;
+    tr = 0.0; ti = 0.0;
+    auto add_if = [&](bool f, double vr, double vi) {
+        const double nr = __dadd_rn(tr, vr), ni = __dadd_rn(ti, vi);
+        tr = f ? nr : tr; ti = f ? ni : ti;
+    };
+    {
+        const unsigned f0 = cframe ? w.flag[ws][P][0] : 0u;
+#pragma unroll
+        for (int k = 1; k <= OL; ++k) {
+            const double2 b = E(0, -k), c = E(0, +k);
+            double vr, vi;
+            online_value(w.wr[ws][P][0][k], w.wi[ws][P][0][k], b.x, b.y, c.x, c.y, vr, vi);
+            add_if((f0 >> k) & 1u, vr, vi);
+        }
+    }
+    online_for_each_pair<Q, P, FOLD>([&](auto rc, auto, auto basec) {
+        constexpr int r = decltype(rc)::value;
+        constexpr int base = decltype(basec)::value;
+        const unsigned f = w.flag[ws][P][r], fn = w.flag[ws][PN][r];
+        add_if(f & 1u, v.r[base], v.i[base]);
+#pragma unroll
+        for (int k = 1; k <= OL; ++k) {
+            if (FOLD == LWSB_FOLD_ANY) {
+                add_if((f >> k) & 1u, v.r[base + 2 * k - 1], v.i[base + 2 * k - 1]);
+                add_if((fn >> k) & 1u, v.r[base + 2 * k], v.i[base + 2 * k]);
+            } else add_if((f >> k) & 1u, v.r[base + k], v.i[base + k]);
+        }
+    });
+}
+
+// bins c0 (residue P0) and c0 + 1 of one row update
+template <int Q, int FOLD, int P0>
+__device__ __forceinline__ void online_two_bins(double2 *ring, int rmask, int pitch, const OnlineW<Q> &w, const LwsbOnlineTask &task,
+                                                int c0, int Nreal, bool act0, bool act1, double a0, double a1)
+{
+    constexpr int L = OL;
+    OnlineVals<Q, FOLD> v0, v1;
+    const OnlineRingCell cell0{ring, rmask, pitch, task.row, L + c0}, cell1{ring, rmask, pitch, task.row, L + c0 + 1};
+    if (act0) online_values<Q, P0, FOLD>(cell0, w, task.which, task.rframe, v0);
+    if (act1) online_values<Q, (P0 + 1) % Q, FOLD>(cell1, w, task.which, task.rframe, v1);
+    double2 *Rrow = ring + (size_t)(task.row & rmask) * pitch;
+    auto commit = [&](int c, double tr, double ti, double a) {
+        double2 val;
+        if (x_project(tr, ti, a, val)) {
+            Rrow[L + c] = val;
+            if (c >= 1 && c <= L) Rrow[L - c] = make_double2(val.x, -val.y);
+            else if (c >= Nreal - 1 - L && c <= Nreal - 2) Rrow[L + 2 * (Nreal - 1) - c] = make_double2(val.x, -val.y);
+        }
+    };
+    if (act0) {
+        double tr, ti;
+        online_accumulate<Q, P0, FOLD>(cell0, w, task.which, task.cframe, v0, tr, ti);
+        commit(c0, tr, ti, a0);
+    }
+    if (act1) {
+        double tr, ti;
+        online_accumulate<Q, (P0 + 1) % Q, FOLD>(cell1, w, task.which, task.cframe, v1, tr, ti);
+        commit(c0 + 1, tr, ti, a1);
+    }
+}
+
+template <int Q, int FOLD>
+__global__ void __launch_bounds__(256)
+k_online_ring2(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *thresholds, int iters, int LA, int R, int pitch,
+               int S, unsigned *status)
+{
+    static_assert(Q <= 4 && Q % 2 == 0, "two bins per step: the first bin of a step has an even residue");
+    extern __shared__ __align__(16) unsigned char online_smem[];
+    double2 *ring = reinterpret_cast<double2 *>(online_smem);
+    __shared__ OnlineW<Q> wsm; // indexed per lane (each lane its own row update): shared memory serves divergent addresses
+    for (int i = threadIdx.x; i < (int)(sizeof(OnlineW<Q>) / 4); i += blockDim.x)
+        reinterpret_cast<unsigned *>(&wsm)[i] = reinterpret_cast<const unsigned *>(&w)[i];
+    __syncthreads();
+    const int u = blockIdx.x;
+    const int T = v.T[u], Nreal = v.Nreal, P = v.P;
+    constexpr int L = OL;
+    const int Np = Nreal + 2 * L, Tp = T + 2 * (Q - 1), rmask = R - 1;
+    double2 *E0 = v.E + v.rowbase[u] * (long long)P + (v.c0 - L); // extended (row 0, column 0)
+    const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
+    const double mean = v.mean_amp[u];
+    const long long n = lwsb_online_chain_len(T, iters, LA);
+    const long long bmax = (long long)S * (n - 1) + (Nreal - 1); // last "bin time": row update j is at bin (bin time - S*j)
+    const int nt = blockDim.x;
+    int lo = 0, hi = -1; // extended rows [lo, hi] are resident
+    long long jc = -1;
+    LwsbOnlineTask task;
+    double thr = 0.0;
+    for (long long bt = 0; bt <= bmax + 1; bt += 2) { // bin time of the first of the step's two bins (S is even: bt % S == 0 is hit)
+        if (bt % S == 0) { // the front of the chain moves to a new row update: residency check (uniform across the CTA)
+            const long long jhi = min(bt / S, n - 1);
+            long long jlo = bt < Nreal ? 0 : (bt - (Nreal - 1) + S - 1) / S;
+            if (jlo > n - 1) jlo = n - 1;
+            const int need_hi = min(Tp - 1, lwsb_online_frame(iters, LA, jhi) + 2 * (Q - 1));
+            const int need_lo = max(0, lwsb_online_frame(iters, LA, jlo) - LA);
+            if (need_hi > hi) {
+                if (need_hi - need_lo + 1 > R && threadIdx.x == 0) atomicCAS(status, 0u, 0xE1000000u | (unsigned)u);
+                for (int e = lo; e < need_lo; ++e) // rows the chain has left: back to global memory
+                    if (e >= Q - 1 && e < T + Q - 1)
+                        for (int x = threadIdx.x; x < Np; x += nt) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+                lo = need_lo;
+                __syncthreads();
+                for (int e = hi + 1; e <= need_hi; ++e) // rows the chain is about to reach
+                    for (int x = threadIdx.x; x < Np; x += nt) ring[(size_t)(e & rmask) * pitch + x] = E0[(long long)e * P + x];
+                hi = need_hi;
+                __syncthreads();
+            }
+        }
+        const long long jhi = bt / S;
+        const long long d = (jhi - threadIdx.x) % nt;
+        const long long j = jhi - (d < 0 ? d + nt : d);
+        if (j >= 0 && j < n) {
+            const int c0 = (int)(bt - (long long)S * j); // even, >= 0
+            if (c0 < Nreal) {
+                if (j != jc) {
+                    jc = j;
+                    task = lwsb_online_decode(T, iters, LA, Q, j);
+                    thr = task.thr < 0 ? 0.0 : __dmul_rn(thresholds[task.thr], mean); // lws.pyx:361, lwslib.cpp:1467
+                }
+                const double *ap = A0 + (long long)task.row * P + L + c0;
+                const double a0 = __ldg(ap), a1 = c0 + 1 < Nreal ? __ldg(ap + 1) : 0.0;
+                const bool act0 = a0 > thr, act1 = c0 + 1 < Nreal && a1 > thr; // lwslib.cpp:295-296
+                if (act0 || act1) {
+                    if (Q == 2 || (c0 & 2) == 0) online_two_bins<Q, FOLD, 0>(ring, rmask, pitch, wsm, task, c0, Nreal, act0, act1, a0, a1);
+                    else online_two_bins<Q, FOLD, 2 % Q>(ring, rmask, pitch, wsm, task, c0, Nreal, act0, act1, a0, a1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = lo; e <= hi; ++e)
+        if (e >= Q - 1 && e < T + Q - 1)
+            for (int x = threadIdx.x; x < Np; x += nt) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+}
+
 template <int Q, int FOLD, int P>
 __device__ __forceinline__ void online_sum_for_residue(int p, const OnlineRingCell &E, const OnlineW<Q> &w, int ws, int rframe,
                                                        int cframe, double &tr, double &ti)
@@ -229,6 +442,17 @@ template <int Q, int FOLD>
 cudaError_t launch_t(const LwsbView &v, const OnlineW<Q> &w, const double *thr, int iters, int LA, int R, int pitch, int S, int nt,
                      size_t bytes, unsigned *status, cudaStream_t s)
 {
+    if constexpr (Q <= 4) {
+        if (S >= 2 + OL && S % 2 == 0) { // two bins per step
+            auto kern2 = k_online_ring2<Q, FOLD>;
+            if (bytes > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                if (e != cudaSuccess) return e;
+            }
+            kern2<<<v.B, nt, bytes, s>>>(v, w, thr, iters, LA, R, pitch, S, status);
+            return cudaGetLastError();
+        }
+    }
     auto kern = k_online_ring<Q, FOLD>;
     if (bytes > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -270,7 +494,9 @@ bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const d
     *err = cudaSuccess;
     const int Q = v.Q;
     if (v.L != OL || !(Q == 2 || Q == 4 || Q == 8)) return false;
-    const int S = (OL + 1 + Q - 1) / Q * Q; // smallest multiple of Q >= L + 1: every thread of a step on the same residue
+    // smallest multiple of Q >= L + 1 (Q > 4: one bin per step) or >= L + 2 (Q <= 4: two bins per step): every thread of a
+    // step on the same residue, and the bins a task takes in one step stay clear of its neighbours' in the chain
+    const int S = Q <= 4 ? (OL + 2 + Q - 1) / Q * Q : (OL + 1 + Q - 1) / Q * Q;
     int span = 0, lastT = -1;
     for (int b = 0; b < v.B; ++b) // exact span for every distinct length of the batch
         if (T_host[b] != lastT) { lastT = T_host[b]; span = std::max(span, online_max_span(lastT, v.Nreal, S, Q, iters, LA)); }

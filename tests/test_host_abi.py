@@ -197,6 +197,73 @@ def test_online_chain_equals_reference_schedule(oracle, name, LA):
     assert relF(got, want) < 1e-12
 
 
+@pytest.mark.parametrize("name,LA", [("q4", 3), ("q2_la4", 4), ("q4_la0", 0), ("q4_la5", 5)])
+def test_online_chain_two_bins_per_step(oracle, name, LA):
+    """k_online_ring2's order: row update j runs S = 8 bins behind row update j-1 and every task takes TWO bins per step
+    (2t - S*j and the next one; S >= 2 + L).  Concurrent semantics: a task reads what the step began with plus its own
+    writes of the step, and no task may read a cell another task writes in the same step."""
+    case = [c for c in SMALL_CASES if c["name"] == name][0]
+    p = lws_b200.lws(*case["args"], **case["kwargs"])
+    po = oracle.lws(*case["args"], **case["kwargs"])
+    Q, L = p.W.shape[1], p.W.shape[2] - 1
+    A0 = np.abs(golden(name)["X"])[:9]
+    T, Nreal = A0.shape
+    iters = 2
+    thr = lws_b200.get_thresholds(iters, 1, 0.1, 1)
+    mean = np.mean(A0)
+    E = dsp.extspec(A0.astype(np.complex128), L, Q)
+    A = np.abs(E)
+    fold = FOLD.get(Q, 0)
+    tabs = {("W", rf): _tables(p.W, fold, rf, 1) for rf in range(2, Q + 1)}
+    tabs["ai"] = _tables(p.W_ai, fold, 1, 0)
+    tabs["af"] = _tables(p.W_af, fold, 1, 1)
+    chain = _native.debug_online_chain(T, iters, LA, Q)
+    S, BPS = 8, 2
+    assert S % Q == 0 and S >= BPS + L
+    for t in range((S * (len(chain) - 1) + Nreal + BPS - 1) // BPS + 1):
+        snap = E.copy()
+        written = {}
+        reads = []
+        for j in range(len(chain)):
+            c0 = BPS * t - S * j
+            if c0 + BPS - 1 < 0 or c0 >= Nreal:
+                continue
+            row, which, rframe, cframe, ti = chain[j]
+            terms = tabs[("W", rframe)] if which == 0 else (tabs["ai"] if which == 1 else tabs["af"])
+            th = 0.0 if ti < 0 else thr[ti] * mean
+            own = {}
+            for c in range(max(c0, 0), min(c0 + BPS, Nreal)):
+                a = A[row, c + L]
+                if not (a > th):
+                    continue
+                dr, dk, co = terms[c % len(terms)]
+                vals = np.empty(len(co), dtype=np.complex128)
+                for q in range(len(co)):
+                    key = (row + dr[q], c + L + dk[q])
+                    if key in own:
+                        vals[q] = own[key]
+                    else:
+                        vals[q] = snap[key]
+                        reads.append(key + (j,))
+                tsum = np.sum(co * vals)
+                if abs(tsum) > 0:
+                    v = tsum * a / abs(tsum)
+                    tg = [((row, c + L), v)]
+                    if 1 <= c <= L:
+                        tg.append(((row, L - c), np.conj(v)))
+                    elif Nreal - 1 - L <= c <= Nreal - 2:
+                        tg.append(((row, L + 2 * (Nreal - 1) - c), np.conj(v)))
+                    for key, vv in tg:
+                        E[key] = vv
+                        own[key] = vv
+                        written[key] = j
+        for (r_, c_, j) in reads:
+            assert written.get((r_, c_), j) == j, "cell read and written by different tasks in one step"
+    got = E[Q - 1:Q - 1 + T, L:L + Nreal]
+    want = po.online_lws(A0, thresholds=thr)
+    assert relF(got, want) < 1e-12
+
+
 def test_nofuture_q4_table_reproduces_reference_indexing(oracle):
     """LWSB_FOLD_NF4 terms applied with the reference's flat offset (m+dr)*Np + 2e + dk, raster order."""
     p, po = lws_b200.lws(32, 8), oracle.lws(32, 8)
