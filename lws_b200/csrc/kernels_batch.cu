@@ -53,7 +53,9 @@ constexpr int pair_thread_cap(int) { return 256; }
 #endif
 // planner cost model of the pair-split kernels (cycles per macro-step: fixed + per warp; weight of the bank-conflict factor)
 constexpr double PAIR_T0 = 8000.0, PAIR_T1 = 500.0, PAIR_TF = 0.3;
+#ifdef LWSB_PAIR_EXPERIMENTS
 constexpr int PAIR_THREADS_MAX = 512;  // pair-split kernels: 15 task warps (240 tasks) + the control warp at 128 registers
+#endif
 constexpr int PAIR_THREADS_PLAN = 256; // what the planner uses: 7 task warps + the control warp keep 255 registers (measured fastest)
 #ifndef LWSB_PAIR_DEFAULT_MODE
 #define LWSB_PAIR_DEFAULT_MODE 1 // odd frame pairs (r = 1, 3) in register windows, no explicit pipelining
@@ -91,10 +93,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_inval(uint64_t *bar)
-{
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
