@@ -188,6 +188,9 @@ int lwsb_debug_terms(const double *wr, const double *wi, int Q, int L, int fold,
  *    lwsb_last_batch_plan) for a shape and a shared-memory / SM budget; returns 0 when the generic kernel serves it. */
 int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, int maxT, int B, long long smem_limit,
                            int sm_count, int force_cluster, int max_sweeps, int force_block, int *out9);
+/*  - lwsb_debug_work_items: the strip kernel's work list for B utterances with active_sweeps[b] sweeps that can move a
+ *    bin: (utterance, pass) pairs, pass-major (utt_pass[2i], utt_pass[2i+1]); returns the number of items. */
+int lwsb_debug_work_items(const int *active_sweeps, int B, int sweeps_per_pass, int max_items, int *utt_pass);
 long long lwsb_debug_online_chain_length(int T, int iterations, int look_ahead);
 int lwsb_debug_online_task(int T, int iterations, int look_ahead, int Q, long long j, int *row, int *which,
                            int *rframe, int *cframe, int *thr_index);

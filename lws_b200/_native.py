@@ -61,6 +61,7 @@ SIGNATURES = {
     "lwsb_last_batch_cycles": (_ci, [_vp, ctypes.POINTER(ctypes.c_ulonglong)]),
     "lwsb_last_batch_trace": (_ci, [_vp, _ci, _ci, _ip, ctypes.POINTER(ctypes.c_ulonglong)]),
     "lwsb_debug_fast_math": (_ci, [_vp, _ll, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "lwsb_debug_work_items": (_ci, [_ip, _ci, _ci, _ci, _ip]),
     "lwsb_debug_online_chain_length": (_ll, [_ci, _ci, _ci]),
     "lwsb_debug_online_task": (_ci, [_ci, _ci, _ci, _ci, _ll, _ip, _ip, _ip, _ip, _ip]),
 }
@@ -365,6 +366,15 @@ def debug_terms(Wc, fold, rframe, cframe, p):
 
 PLAN_KEYS = ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots", "sweeps_per_pass", "ring_rows",
              "ring_pitch", "threads", "smem_bytes", "sweep_lag", "sweep_fastest", "tensor_memory", "block_bins")
+
+
+def debug_work_items(active_sweeps, sweeps_per_pass):
+    """The strip kernel's work list [(utterance, pass), ...] for the given numbers of active sweeps per utterance."""
+    a = (ctypes.c_int * len(active_sweeps))(*[int(x) for x in active_sweeps])
+    n = _check(lib().lwsb_debug_work_items(a, len(active_sweeps), int(sweeps_per_pass), 0, None))
+    out = (ctypes.c_int * (2 * max(n, 1)))()
+    _check(lib().lwsb_debug_work_items(a, len(active_sweeps), int(sweeps_per_pass), n, out))
+    return [(out[2 * i], out[2 * i + 1]) for i in range(n)]
 
 
 def debug_plan_strips(Nreal, Q, L, iterations, maxT, B, smem_limit=232448, sm_count=148, cluster=0, sweeps=0, block=0):

@@ -41,6 +41,22 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Work list of the strip kernel: one item (utterance, pass) per pass of G sweeps an utterance needs, PASS-MAJOR, so that
+// an item's producer -- the previous pass of the same utterance -- always has a smaller index: clusters take items in
+// increasing order, hence the producer is finished or running whenever an item waits for it.  Returns the largest
+// number of passes of any utterance.
+int build_work_items(const int *nact, int B, int G, std::vector<int> &items)
+{
+    int max_pass = 0;
+    items.clear();
+    for (int pass = 0, more = 1; more; ++pass) {
+        more = 0;
+        for (int b = 0; b < B; ++b)
+            if (pass * G < nact[b]) { items.push_back(b); items.push_back(pass); more = 1; max_pass = pass + 1; }
+    }
+    return max_pass;
+}
+
 std::mutex &strip_mutex(int device)
 {
     static std::mutex m[64];
@@ -455,12 +471,7 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
         // work list: one item per (utterance, pass of pl.G sweeps), pass-major, so that the passes of one utterance
         // run on different clusters at the same time, each a few frames behind the previous one
         std::vector<int> items;
-        int max_pass = 0;
-        for (int pass = 0, more = 1; more; ++pass) {
-            more = 0;
-            for (int b = 0; b < c->B; ++b)
-                if (pass * pl.G < nact[b]) { items.push_back(b); items.push_back(pass); more = 1; max_pass = pass + 1; }
-        }
+        const int max_pass = build_work_items(nact.data(), c->B, pl.G, items);
         const int n_items = (int)(items.size() / 2);
         const size_t done_bytes = (size_t)c->B * std::max(max_pass, 1) * STRIP_MAX_CLUSTER * sizeof(unsigned);
         if (n_items > 0) {
@@ -1026,6 +1037,16 @@ extern "C" int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, i
     const int v[13] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM, p.SBK};
     for (int i = 0; i < 13; ++i) out9[i] = v[i];
     return 1;
+}
+
+extern "C" int lwsb_debug_work_items(const int *active_sweeps, int B, int sweeps_per_pass, int max_items, int *utt_pass)
+{
+    if (!active_sweeps || B < 1 || sweeps_per_pass < 1 || max_items < 0 || (max_items > 0 && !utt_pass)) return LWSB_ERR_ARG;
+    std::vector<int> items;
+    build_work_items(active_sweeps, B, sweeps_per_pass, items);
+    const int n = (int)(items.size() / 2);
+    for (int i = 0; i < 2 * std::min(n, max_items); ++i) utt_pass[i] = items[i];
+    return n;
 }
 
 extern "C" long long lwsb_debug_online_chain_length(int T, int iterations, int look_ahead)

@@ -235,3 +235,19 @@ def test_planner_properties():
                         assert R * pl["ring_pitch"] * 16 + R * 8 + 32 + 4 * iters <= pl["smem_bytes"]
     assert _native.debug_plan_strips(513, 3, 5, 10, 100, 1) is None     # Q must divide the block size
     assert _native.debug_plan_strips(513, 4, 7, 10, 100, 1) is None     # L is fixed at 5
+
+
+def test_work_items_are_pass_major_and_producers_come_first():
+    """The strip kernel's work list: every pass of every utterance exactly once, and the previous pass of the same
+    utterance always earlier in the list (clusters take items in increasing order, so a waiting item's producer is
+    finished or running: no dead-lock)."""
+    rng = np.random.default_rng(5)
+    for B, G in ((1, 7), (5, 3), (64, 7), (9, 1), (3, 100)):
+        act = [int(x) for x in rng.integers(0, 101, B)]
+        act[0] = 100
+        items = _native.debug_work_items(act, G)
+        want = {(b, ps) for b in range(B) for ps in range((act[b] + G - 1) // G)}
+        assert len(items) == len(want) and set(items) == want
+        pos = {it: i for i, it in enumerate(items)}
+        assert all(pos[(b, ps - 1)] < pos[(b, ps)] for (b, ps) in items if ps > 0)
+        assert [ps for _, ps in items] == sorted(ps for _, ps in items)   # pass-major
