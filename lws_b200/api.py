@@ -11,6 +11,7 @@ impossible in the reference, so they cannot collide):
 """
 from __future__ import annotations
 
+import os
 import threading
 
 import numpy as np
@@ -23,12 +24,23 @@ _ctx_lock = threading.Lock()
 _contexts = {}
 
 
-def _context(device):
+def _context(device, slot=0):
+    """One context (stream, device buffers) per (device, slot); slot 1 is the second half of an overlapped batch."""
+    key = device if slot == 0 else (device, slot)
     with _ctx_lock:
-        c = _contexts.get(device)
+        c = _contexts.get(key)
         if c is None:
-            c = _contexts[device] = _native.Context(device)
+            c = _contexts[key] = _native.Context(device)
         return c
+
+
+# Optional (LWSB_OVERLAP_MIN=n, off by default): a batch of at least n utterances on ONE device is cut in two (58 % / 42 %)
+# and handled by two host threads with a context each, so that the second half's host-to-device copy and pre-processing
+# overlap the first half's sweeps and the first half's device-to-host copy overlaps the second half's sweeps (the strip
+# kernels themselves run one after the other, lws_b200.h).  Measured on B200 at BASELINE configs[1]: 125 ms per call
+# against 120 ms without it -- two launches of 37 / 27 utterances fill the 74 clusters' rounds of work items worse than
+# one launch of 64, which costs more than the ~5 ms of copies it hides.
+OVERLAP_MIN = int(os.environ.get("LWSB_OVERLAP_MIN", "0"))
 
 
 def _devices(device):
@@ -120,22 +132,26 @@ def _shard(n, k):
     return [(b[i], b[i + 1]) for i in range(k)]
 
 
-def _run_sharded(devices, arrs, outs, fn):
+def _run_sharded(devices, arrs, outs, fn, overlap=False):
     """fn(ctx, arrays, outs) on each device's contiguous share; one host thread per GPU
     (ctypes releases the GIL, so the GPUs run concurrently)."""
     parts = _shard(len(arrs), len(devices))
+    slots = [0] * len(parts)
+    if len(parts) == 1 and overlap and OVERLAP_MIN > 0 and len(arrs) >= OVERLAP_MIN:
+        cut = (len(arrs) * 58 + 99) // 100
+        parts, devices, slots = [(0, cut), (cut, len(arrs))], [devices[0], devices[0]], [0, 1]
     if len(parts) == 1:
         fn(_context(devices[0]), arrs, outs)
         return
     errs = []
 
-    def work(dev, lo, hi):
+    def work(dev, slot, lo, hi):
         try:
-            fn(_context(dev), arrs[lo:hi], outs[lo:hi])
+            fn(_context(dev, slot), arrs[lo:hi], outs[lo:hi])
         except BaseException as e:  # re-raised in the caller
             errs.append(e)
 
-    ts = [threading.Thread(target=work, args=(devices[i], lo, hi)) for i, (lo, hi) in enumerate(parts)]
+    ts = [threading.Thread(target=work, args=(devices[i], slots[i], lo, hi)) for i, (lo, hi) in enumerate(parts)]
     [t.start() for t in ts]
     [t.join() for t in ts]
     if errs:
@@ -155,7 +171,7 @@ def batch_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=
         ctx.set_weights(_native.W, W)
         ctx.batch_lws(a, kind, thresholds, flags, outs=o)
 
-    _run_sharded(_devices(device), arrs, outs, fn)
+    _run_sharded(_devices(device), arrs, outs, fn, overlap=True)
     return _rebuild(outs, shape, out)
 
 
