@@ -462,3 +462,22 @@ def test_consistency_on_device(gpu, oracle):
     from lws_b200 import transforms
     both = transforms.get_consistency(np.stack([S, S[::-1]]), 512, 128, pg.awin, pg.swin, perfectrec=True)
     assert both.shape == (2,) and abs(both[0] - po.get_consistency(S)) < 1e-8
+
+
+def test_batch_sharded_over_two_gpus_in_one_process(gpu, oracle):
+    """device=[0, 1]: utterances split contiguously over the GPUs, one host thread and context per device, no collective
+    (skipped on a single-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    po = oracle.lws(512, 128)
+    p2 = gpu.lws(512, 128, device=[0, 1])
+    As = [np.abs(po.stft(make_signal("tonal" if i % 2 else "white", 70 + i, 4000 + 500 * (i % 5)))) for i in range(9)]
+    thr = gpu.get_thresholds(8, 2.0, 0.2, 1)
+    Ys = p2.batch_lws(As, thresholds=thr)
+    for A, Y in zip(As, Ys):
+        _close(Y, po.batch_lws(A, thresholds=thr), "two-GPU shard")
+    Yr = p2.run_lws(As[:4])
+    p1 = gpu.lws(512, 128)
+    for a, b in zip(Yr, p1.run_lws(As[:4])):
+        assert np.array_equal(a, b)
