@@ -136,7 +136,10 @@ class Context(object):
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().lwsb_destroy(self._h)
+            try:
+                lib().lwsb_destroy(self._h)
+            except TypeError:  # interpreter shutdown: the module globals are already gone, the driver reclaims the context
+                pass
             self._h = None
 
     __del__ = close
