@@ -206,6 +206,20 @@ def test_cfg2_one_utterance_vs_oracle(gpu, oracle):
     _close(pg.batch_lws(A), po.batch_lws(A), "cfg2 batch")
 
 
+def test_cfg3_cfg4_one_utterance_vs_oracle(gpu, oracle):
+    """One utterance of configs[2] / configs[3] at full size (628 x 513, mode='music': NoFuture_LWSQ4, TF-RTISI-LA with
+    look-ahead 3 and 10 iterations -- 25 688 row updates -- and the full run_lws chain) against the oracle (~3 s CPU)."""
+    po, pg = oracle.lws(1024, 256, mode="music"), gpu.lws(1024, 256, mode="music")
+    A = np.abs(po.stft(make_signal("white", 3003, 160000)))
+    assert A.shape == (628, 513)
+    _close(pg.nofuture_lws(A), po.nofuture_lws(A), "cfg3 nofuture")
+    _close(pg.online_lws(A), po.online_lws(A), "cfg3 online")
+    _close(pg.run_lws(A), po.run_lws(A), "cfg4 run_lws")
+    # a batch of three: every member equals the single-utterance result
+    Ys = pg.online_lws(np.stack([A, A[::-1], A]))
+    assert np.array_equal(Ys[0], pg.online_lws(A)) and np.array_equal(Ys[0], Ys[2])
+
+
 def test_q8_large_frame_vs_oracle(gpu, oracle):
     """configs[4] geometry (2048-pt, hop 256, Q = 8) at reduced length and 10 iterations."""
     po, pg = oracle.lws(2048, 256), gpu.lws(2048, 256)
