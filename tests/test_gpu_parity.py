@@ -248,6 +248,9 @@ STRIP_CASES = [  # fsize, hop, samples, iterations, cluster, sweeps per pass, sm
     (1024, 256, 30000, 12, 2, 0, 0), (1024, 256, 30000, 12, 4, 0, 0), (1024, 256, 30000, 12, 8, 0, 0),
     (1024, 256, 30000, 9, 8, 2, 0), (2048, 256, 40000, 8, 4, 0, 0), (2048, 256, 40000, 8, 8, 0, 0),
     (128, 64, 9000, 10, 1, 0, 0), (128, 64, 9000, 10, 2, 3, 0), (512, 128, 32000, 100, 0, 0, 0),
+    # one sweep per pass: as many passes as sweeps, all in flight on different clusters, each reading what the previous one
+    # wrote a few frames earlier (the tightest use of the progress counters)
+    (512, 128, 32000, 40, 2, 1, 0), (1024, 256, 60000, 24, 4, 1, 0), (512, 128, 32000, 30, 1, 1, 0),
 ]
 
 
