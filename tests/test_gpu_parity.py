@@ -498,3 +498,24 @@ def test_batch_sharded_over_two_gpus_in_one_process(gpu, oracle):
     p1 = gpu.lws(512, 128)
     for a, b in zip(Yr, p1.run_lws(As[:4])):
         assert np.array_equal(a, b)
+
+
+def test_many_short_utterances_more_work_items_than_clusters(gpu, oracle):
+    """300 ragged utterances, 3 sweeps per pass: ~1200 work items dealt to the resident clusters in several rounds."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(512, 128), gpu.lws(512, 128)
+    rng = np.random.default_rng(17)
+    As = [np.abs(po.stft(make_signal("white" if i % 3 else "tonal", 300 + i, int(rng.integers(1500, 6000))))) for i in range(300)]
+    thr = gpu.get_thresholds(12, 2.0, 0.15, 1)
+    try:
+        ctx.set_tuning(0, 2, 3)
+        Ys = pg.batch_lws(As, thresholds=thr)
+        plan = ctx.last_batch_plan()
+        assert plan is not None and plan["sweeps_per_pass"] <= 3
+    finally:
+        ctx.set_tuning(0, 0, 0)
+    for i in range(0, 300, 7):
+        _close(Ys[i], po.batch_lws(As[i], thresholds=thr), "utterance %d of 300" % i)
+    one = pg.batch_lws(As[123], thresholds=thr)
+    assert np.array_equal(one, Ys[123])
