@@ -223,7 +223,7 @@ class Ranks(object):
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29500")
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
+            os.environ.pop("NCCL_DEBUG", None)  # no NCCL banner (stdout is guarded as well, see main())
             if backend == "nccl":
                 dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             else:
@@ -400,9 +400,26 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.impl == "reference":
-        return run_reference_arm(args)
-    return run_b200_arm(args)
+    # ONE JSON line on stdout, whatever the libraries underneath print (NCCL writes its version banner to fd 1): file
+    # descriptor 1 points at stderr while the arm runs, and the arm's own print() calls are collected and replayed
+    # on the real stdout afterwards.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    buf = io.StringIO()
+    sys.stdout = buf
+    try:
+        rc = run_reference_arm(args) if args.impl == "reference" else run_b200_arm(args)
+    finally:
+        sys.stdout = sys.__stdout__
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        lines = [l for l in buf.getvalue().splitlines() if l.strip()]
+        for l in lines:
+            print(l, flush=True)
+    return rc
 
 
 if __name__ == "__main__":
