@@ -21,8 +21,15 @@
 //     after every macro-step the control warp publishes the strip's progress to both
 //     neighbours (st.release.cluster) and polls theirs (ld.acquire.cluster) while the compute
 //     warps work on the next macro-step.
+//   * The passes of an utterance are WORK ITEMS dealt to the resident clusters in turn: a pass reads each frame from
+//     global memory after the previous pass of the same utterance -- usually running on another cluster at the same
+//     time -- has written it back (per-strip progress counters, st.release.gpu / ld.acquire.gpu around the TMA
+//     traffic), so one utterance keeps ceil(active/G) clusters busy and a batch keeps every SM busy.
 //   * Arithmetic is the reference's, operation for operation (exact.cuh): results are
-//     bit-identical to lwslib's LWSQ2 / LWSQ4 / LWSanyQ.
+//     bit-identical to lwslib's LWSQ2 / LWSQ4 / LWSanyQ.  sqrt and the divisions are the correctly rounded fast
+//     paths without their slow-path branches (fast_math.cuh).
+// Files: this one holds the PTX helpers, the planner and the dispatch; strip_body.inc the block update, the kernel and
+// its launch code, compiled for 8- and for 4-bin blocks; strip_pair.cuh the two-lanes-per-task variant.
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <algorithm>
