@@ -251,3 +251,18 @@ def test_work_items_are_pass_major_and_producers_come_first():
         pos = {it: i for i, it in enumerate(items)}
         assert all(pos[(b, ps - 1)] < pos[(b, ps)] for (b, ps) in items if ps > 0)
         assert [ps for _, ps in items] == sorted(ps for _, ps in items)   # pass-major
+
+
+def test_planner_picks_the_measured_best_plans_for_the_baseline_shapes():
+    """The cost model was fitted on B200: for BASELINE configs[1] (67 of 100 sweeps can move a bin with
+    the default thresholds) and all-active it must land on the plan measured fastest -- cluster 2, 7 sweeps per pass,
+    8-bin blocks -- and for configs[4] (Q = 8, 4 utterances per GPU) on cluster 8; 4-bin blocks only on request."""
+    for active in (67, 100):
+        pl = _native.debug_plan_strips(513, 4, 5, active, 628, 64)
+        assert (pl["cluster"], pl["sweeps_per_pass"], pl["block_bins"], pl["sweep_lag"]) == (2, 7, 8, 4), pl
+    pl = _native.debug_plan_strips(1025, 8, 5, 150, 5632, 4)
+    assert pl["cluster"] == 8 and pl["block_bins"] == 8 and pl["sweep_lag"] >= 8, pl
+    assert _native.debug_plan_strips(513, 4, 5, 67, 628, 64, block=4)["block_bins"] == 4
+    # a single utterance: several passes in flight on different clusters rather than all sweeps in one pass
+    pl = _native.debug_plan_strips(513, 4, 5, 67, 628, 1)
+    assert (67 + pl["sweeps_per_pass"] - 1) // pl["sweeps_per_pass"] >= 4, pl
