@@ -3,11 +3,13 @@
 path timed beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload cfg1|cfg2|cfg5] [--thresholds default|zero] [--cpu-seconds S]
+                    [--workload cfg1|cfg2|cfg3|cfg4|cfg5] [--thresholds default|zero] [--cpu-seconds S]
 
-A *step* is one full ``batch_lws`` call on one batch of synthetic magnitude spectrograms
+A *step* is one full call of the workload's hot path on one batch of synthetic magnitude spectrograms
 (BASELINE.json configs[1] by default: 64 utterances x 10 s at 16 kHz, 1024-pt STFT, hop 256,
-100 iterations, default thresholds).  One JSON line on stdout (rank 0):
+batch_lws with 100 iterations, default thresholds; cfg3 = configs[2]: nofuture_lws + online_lws in RTISI-LA mode;
+cfg4 = configs[3]: the full run_lws chain, 32 utterances per GPU = 256 over 8; cfg5 = configs[4]: 2048-pt frames,
+200 iterations, 4 utterances per GPU = 32 over 8).  One JSON line on stdout (rank 0):
 
 * ``value``   bins/s with the magnitudes already resident in HBM: lwsb_load (extend, |.|, mean)
               + the sweep kernel + lwsb_store (crop) per step, CUDA events on the launching
@@ -39,18 +41,47 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (config index in BASELINE.json, utterances, samples, fsize, hop, iterations)
+    # name: (config index in BASELINE.json, utterances per GPU, samples, fsize, hop, batch iterations)
     "cfg1": (0, 1, 32000, 512, 128, 100),
     "cfg2": (1, 64, 160000, 1024, 256, 100),
-    "cfg5": (4, 4, 1440000, 2048, 256, 200),
+    "cfg3": (2, 64, 160000, 1024, 256, 0),     # mode='music' without the batch stage: nofuture 1 sweep + online 10 iterations, LA 3
+    "cfg4": (3, 32, 160000, 1024, 256, 100),   # mode='music': nofuture -> online -> batch; 256 utterances over 8 GPUs
+    "cfg5": (4, 4, 1440000, 2048, 256, 200),   # 32 utterances over 8 GPUs
 }
-ALGO_BYTES_PER_BIN_ITER = 40.0  # 16 B read + 16 B write of the complex128 state + 8 B amplitude
+MUSIC = ("cfg3", "cfg4")                         # workloads run with lws.lws(..., mode='music') (lws.pyx:432-437)
+STAGES = {"cfg3": "nofuture_lws + online_lws", "cfg4": "run_lws: nofuture -> online -> batch"}
+ALGO_BYTES_PER_BIN_ITER = 40.0  # 16 B read + 16 B write of the complex128 state + 8 B amplitude (SURVEY.md section 8d)
+FLOP_PER_ACTIVE_BIN = {2: 100.0, 4: 270.0, 8: 902.0}  # separately rounded fp64 operations per updated bin (batch sweeps, default windows):
+                                                       # Q = 4 folded: 256 adds / multiplies + projection; Q = 8: 74 terms x 12 + projection
+
+
+def metric_name(name):
+    it = WORKLOADS[name][5]
+    if name in MUSIC:
+        return "spectrogram bins/sec (%s)" % STAGES[name]
+    return "spectrogram bins/sec (batch_lws, %d iters)" % it
+
+
+def make_plugin(mod, name, **kw):
+    """the reference-API object of the workload: lws.lws(fsize, hop[, mode='music'][, batch_iterations=0])"""
+    idx, B, n, fs, hop, it = WORKLOADS[name]
+    if name in MUSIC:
+        return mod.lws(fs, hop, mode="music", batch_iterations=it, **kw)
+    return mod.lws(fs, hop, **kw)
+
+
+def hot_path(p, name, A, thr, **kw):
+    """one call of the workload's hot path through the reference API"""
+    if name in MUSIC:
+        return p.run_lws(A, **kw)       # nofuture -> online (-> batch when batch_iterations > 0), lws.pyx:495-499
+    return p.batch_lws(A, thresholds=thr, **kw)
 
 
 def workload_desc(name, thresholds):
     idx, B, n, fs, hop, it = WORKLOADS[name]
-    return {"workload": "BASELINE.json configs[%d]: %d utterances x %d samples, %d-pt STFT hop %d, batch_lws %d iters, "
-                        "%s thresholds" % (idx, B, n, fs, hop, it, thresholds),
+    what = ("batch_lws %d iters, %s thresholds" % (it, thresholds)) if name not in MUSIC else (
+        "mode='music' (nofuture 1 iter, online 10 iters, look-ahead 3)" + (", batch %d iters" % it if it else ", no batch stage") + ": " + STAGES[name])
+    return {"workload": "BASELINE.json configs[%d]: %d utterances x %d samples per GPU, %d-pt STFT hop %d, %s" % (idx, B, n, fs, hop, what),
             "utterances_per_gpu": B, "fsize": fs, "hop": hop, "iterations": it, "thresholds": thresholds,
             "l2": "state per step (extended spectrogram + amplitude, fp64) is larger than the 126 MB L2"
                   if name != "cfg1" else "L2 flushed between steps"}
@@ -97,8 +128,10 @@ def _cpu_worker(args):
     mod, _ = load_reference()
     idx, B, n, fs, hop, it = WORKLOADS[name]
     A = _CPU_INPUTS[b]
+    p = make_plugin(mod, name)
+    thr = thresholds_for(name, thr_mode)
     t0 = time.perf_counter()
-    mod.lws(fs, hop).batch_lws(A, thresholds=thresholds_for(name, thr_mode))
+    hot_path(p, name, A, thr)
     return time.perf_counter() - t0, A.size
 
 
@@ -106,7 +139,7 @@ def cpu_baseline_one_core(name, thr_mode, budget_s):
     """bins/s of the reference on ONE core over a bounded sample of the workload's utterances."""
     mod, kind = load_reference()
     idx, B, n, fs, hop, it = WORKLOADS[name]
-    p = mod.lws(fs, hop)
+    p = make_plugin(mod, name)
     thr = thresholds_for(name, thr_mode)
     bins, secs, used = 0, 0.0, 0
     for b in range(B):
@@ -115,7 +148,7 @@ def cpu_baseline_one_core(name, thr_mode, budget_s):
         if name == "cfg5":  # 158 s per utterance: time a 1/16 slice of the frames instead
             A = A[: A.shape[0] // 16]
         t0 = time.perf_counter()
-        p.batch_lws(A, thresholds=thr)
+        hot_path(p, name, A, thr)
         secs += time.perf_counter() - t0
         bins += A.size
         used += 1
@@ -136,7 +169,7 @@ def run_reference_arm(args):
     mod, kind = load_reference()
     cores = os.cpu_count() or 1
     per_step = min(cores, B)
-    p = mod.lws(fs, hop)
+    p = make_plugin(mod, name)
     for b in range(per_step):  # untimed set-up: the step times the hot path, not input synthesis
         A = np.abs(p.stft(np.random.default_rng(1000 * (idx + 1) + b).standard_normal(n)))
         _CPU_INPUTS[b] = A[: A.shape[0] // 16] if name == "cfg5" else A
@@ -159,7 +192,7 @@ def run_reference_arm(args):
     value = bins_step * steps / tot
     sample = "%d utterances of the workload per step on %d processes%s" % (
         per_step, min(cores, per_step), " (first 1/16 of the frames of each)" if name == "cfg5" else "")
-    line = {"impl": "reference", "metric": "spectrogram bins/sec (batch_lws, %d iters)" % it, "value": value,
+    line = {"impl": "reference", "metric": metric_name(name), "value": value,
             "unit": "bins/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_desc(name, args.thresholds),
@@ -223,7 +256,8 @@ class Ranks(object):
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29500")
-            os.environ.pop("NCCL_DEBUG", None)  # no NCCL banner (stdout is guarded as well, see main())
+            # (NCCL_DEBUG is left as the launcher set it: main() points fd 1 at stderr while the arm runs, so
+            # NCCL's banner cannot reach the JSON line, and the driver can read the rank check from stderr)
             if backend == "nccl":
                 dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             else:
@@ -261,6 +295,22 @@ def throughput(units_per_rank_step, steps, world_units_factor, seconds_max):
     return units_per_rank_step * world_units_factor * steps / seconds_max
 
 
+def active_bin_iters(A, thr):
+    """exact number of bin updates a batch_lws call performs: bins with |S| > thresholds[i] * mean|S| (lwslib.cpp:295-296),
+    summed over sweeps and utterances"""
+    total = 0
+    for b in range(A.shape[0]):
+        a = np.sort(A[b].ravel())
+        lim = thr * np.mean(A[b])
+        total += int((a.size - np.searchsorted(a, lim, side="right")).sum())
+    return total
+
+
+def online_chain_len(T, it, LA):
+    """row updates of TF_RTISI_LA (lwslib.cpp:1432-1491): sum over frames of 1 + it * (min(LA, m) + 1)"""
+    return sum(1 + it * (min(LA, m) + 1) for m in range(T))
+
+
 def run_b200_arm(args):
     import torch
     import lws_b200
@@ -273,8 +323,13 @@ def run_b200_arm(args):
     world, rank, local = ranks.world, ranks.rank, ranks.local
     name = args.workload
     idx, B, n, fs, hop, it = WORKLOADS[name]
+    music = name in MUSIC
     thr = thresholds_for(name, args.thresholds)
-    p = lws_b200.lws(fs, hop, device=local)
+    p = make_plugin(lws_b200, name, device=local)
+    nf_thr = lws_b200.get_thresholds(p.nofuture_iterations, p.nofuture_alpha, p.nofuture_beta, p.nofuture_gamma)
+    on_thr = lws_b200.get_thresholds(p.online_iterations, p.online_alpha, p.online_beta, p.online_gamma)
+    if music:
+        thr = lws_b200.get_thresholds(it, p.batch_alpha, p.batch_beta, p.batch_gamma)  # what run_lws uses (lws.pyx:487-499)
 
     # synthetic magnitudes (untimed set-up): |STFT| of white noise, computed by the library's own stft
     x = signals(name, rank)
@@ -286,6 +341,9 @@ def run_b200_arm(args):
     stream = torch.cuda.current_stream()
     ctx = _native.Context(local, stream.cuda_stream)
     ctx.set_weights(_native.W, p.W)
+    if music:
+        ctx.set_weights(_native.W_AI, p.W_ai)
+        ctx.set_weights(_native.W_AF, p.W_af)
     A_dev = torch.from_numpy(A_host).cuda()
     Y_dev = torch.empty((Bn, T, Nreal), dtype=torch.complex128, device="cuda")
     in_ptrs = [A_dev[b].data_ptr() for b in range(Bn)]
@@ -294,9 +352,12 @@ def run_b200_arm(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if name == "cfg1" else None
 
     def step_device():
-        ctx.load_device(in_ptrs, Ts, Nreal, _native.F64)
-        ctx.batch(thr)
-        ctx.store_device(out_ptrs)
+        if music:
+            ctx.run_lws_device(in_ptrs, out_ptrs, Ts, Nreal, _native.F64, nf_thr, on_thr, p.look_ahead, thr)
+        else:
+            ctx.load_device(in_ptrs, Ts, Nreal, _native.F64)
+            ctx.batch(thr)
+            ctx.store_device(out_ptrs)
 
     barrier = ranks.barrier
 
@@ -308,7 +369,7 @@ def run_b200_arm(args):
     barrier()
     l0 = ctx.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kernel_ms = []
+    stage_ms = []
     t_wall0 = time.perf_counter()
     ev[0].record(stream)
     dev_ms = 0.0
@@ -316,7 +377,7 @@ def run_b200_arm(args):
         if flush is not None:
             flush.fill_(1)
         step_device()
-        kernel_ms.append(ctx.last_compute_ms())
+        stage_ms.append(ctx.last_stage_ms())
     ev[1].record(stream)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
@@ -326,6 +387,9 @@ def run_b200_arm(args):
     dev_ms_max = ranks.max(dev_ms)
     bins_all = ranks.sum(bins_rank)  # every rank holds its own utterances (weak scaling)
     value = throughput(bins_all / world, args.steps, world, dev_ms_max * 1e-3)
+    work = ctx.last_batch_work() if it > 0 else None
+    plan = ctx.last_batch_plan() if it > 0 else None
+    cycles = ctx.last_batch_cycles() if it > 0 else None
 
     # ---- e2e: public API, pinned host in/out, H2D + D2H inside the timed region
     A_pin = torch.from_numpy(A_host).pin_memory()
@@ -333,19 +397,31 @@ def run_b200_arm(args):
     A_np, Y_np = A_pin.numpy(), Y_pin.numpy()
     e2e_warm = max(1, min(args.warmup, 2))
     for _ in range(e2e_warm):
-        p.batch_lws(A_np, thresholds=thr, out=Y_np)
+        hot_path(p, name, A_np, thr, out=Y_np)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        p.batch_lws(A_np, thresholds=thr, out=Y_np)
+        hot_path(p, name, A_np, thr, out=Y_np)
         chk = float(np.abs(Y_np[0, 0, 0]))  # the step's result is read on the host
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_value = throughput(bins_all / world, args.steps, world, ranks.max(e2e_s))
 
+    # the plain drop-in call: pageable numpy in, fresh numpy out (what a user of the reference writes)
+    A_page = np.array(A_host)
+    hot_path(p, name, A_page, thr)
+    barrier()
+    t0 = time.perf_counter()
+    nplain = max(1, min(args.steps, 3))
+    for _ in range(nplain):
+        Y_plain = hot_path(p, name, A_page, thr)
+    plain_s = (time.perf_counter() - t0) / nplain
+    plain_s = ranks.max(plain_s)
+
     # sanity: device-resident and host paths agree bit for bit, magnitudes preserved
     Yd = Y_dev.cpu().numpy()
     assert np.array_equal(Yd, Y_np), "device-resident and host-API results differ"
+    assert np.array_equal(np.asarray(Y_plain), Y_np), "plain-call and pinned-buffer results differ"
     assert np.allclose(np.abs(Y_np[0]), A_host[0], rtol=1e-10, atol=1e-12 * A_host.max())
 
     if rank == 0:
@@ -355,33 +431,67 @@ def run_b200_arm(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        k_ms = statistics.mean(kernel_ms)
-        achieved = ALGO_BYTES_PER_BIN_ITER * bins_rank * it / (k_ms * 1e-3) / 1e9
+        stages = {k: statistics.mean([m[k] for m in stage_ms]) for k in ("nofuture", "online", "batch") if stage_ms[0][k] is not None}
+        # algorithmic bytes per launch of each stage: 40 B per bin per row update
+        rows = {"nofuture": Bn * T * len(nf_thr), "online": Bn * online_chain_len(T, len(on_thr), p.look_ahead) if len(on_thr) else 0,
+                "batch": Bn * T * it}
+        dom = max(stages, key=lambda k: stages[k])
+        k_ms = stages[dom]
+        algo_bytes = ALGO_BYTES_PER_BIN_ITER * rows[dom] * Nreal
+        achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
+                "unit": "GB/s", "frac": achieved / peak,
+                "kernel": {"batch": "batch sweep kernel (k_batch_strips)", "online": "online chain kernel (k_online_ring*)",
+                           "nofuture": "no-future sweep kernel"}[dom],
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "algorithmic_bytes_definition": "40 B x bins x row updates asked for, independent of thresholding (SURVEY.md section 8d)",
+                "stage_ms": stages,
+                "stage_frac": {k: ALGO_BYTES_PER_BIN_ITER * rows[k] * Nreal / (stages[k] * 1e-3) / 1e9 / peak for k in stages},
+                "note": "bit-exact fp64 Gauss-Seidel stencil: bounded by shared-memory bandwidth and fp64 issue, not by HBM "
+                        "(DESIGN.md section 5); fp64_frac is the fraction of the non-FMA fp64 issue peak"}
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % name)
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch")
+            roof["traffic_source"] = "%s (ncu --set full, builder run: %s)" % (os.path.relpath(tp, ROOT), tj.get("source", "see profiles/README.md"))
+        roof["traffic"] = traffic
+        if it > 0 and "batch" in stages:
+            Q = fs // hop
+            sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+            sms = ctx.device_info()["sm_count"]
+            fp64_peak = sms * 64 * sm_mhz * 1e6          # separately rounded fp64 operations per second (no FMA: the reference has none)
+            act = active_bin_iters(A_host, thr)
+            flops = FLOP_PER_ACTIVE_BIN.get(Q, 0.0) * act
+            roof["fp64_frac"] = flops / (stages["batch"] * 1e-3) / fp64_peak
+            roof["fp64_peak_ops"] = fp64_peak
+            roof["fp64_ops_per_active_bin"] = FLOP_PER_ACTIVE_BIN.get(Q)
+            roof["bin_iters"] = {"asked": int(bins_rank) * it, "in_sweeps_executed": work["bin_iters_executed"] if work else None,
+                                 "active_bins_updated": act}
+            if work and work["bin_iters_executed"]:
+                roof["achieved_executed_sweeps"] = ALGO_BYTES_PER_BIN_ITER * work["bin_iters_executed"] / (stages["batch"] * 1e-3) / 1e9
+                roof["frac_executed_sweeps"] = roof["achieved_executed_sweeps"] / peak
         cpu = cpu_baseline_one_core(name, args.thresholds, args.cpu_seconds)
         line = {
-            "metric": "spectrogram bins/sec (batch_lws, %d iters)" % it, "value": value, "unit": "bins/s",
+            "metric": metric_name(name), "value": value, "unit": "bins/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_desc(name, args.thresholds),
-            "bin_iters_per_s": value * it,
+            "bin_iters_per_s": value * max(it, 1),
             "e2e": {"value": e2e_value, "unit": "bins/s", "h2d_bytes_per_step": int(A_host.nbytes),
                     "d2h_bytes_per_step": int(Y_np.nbytes), "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "lws_b200.lws(%d, %d).batch_lws(A, out=Y), pinned host numpy in/out" % (fs, hop)},
+                    "api": "lws_b200.%s, pinned host numpy in/out" % (
+                        ("lws(%d, %d, mode='music', batch_iterations=%d).run_lws(A, out=Y)" % (fs, hop, it)) if music
+                        else ("lws(%d, %d).batch_lws(A, out=Y)" % (fs, hop))),
+                    "plain_call_ms": 1e3 * plain_s,
+                    "plain_call": "the same call with pageable numpy in and a fresh numpy result (no out=)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
-                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "batch sweep kernel", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_BIN_ITER * bins_rank * it,
-                         "note": "bit-exact fp64 Gauss-Seidel stencil: bounded by shared-memory bandwidth and in-order fp64 issue of the few warps the ring leaves room for, not by HBM (DESIGN.md section 5)"},
+            "roofline": roof,
             "cpu_baseline": cpu,
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
-            "plan": ctx.last_batch_plan(), "cycles_cluster0": ctx.last_batch_cycles(),
-            "kernel_share_of_step": k_ms * args.steps / dev_ms if dev_ms else None,
+            "plan": plan, "cycles_cluster0": cycles,
+            "kernel_share_of_step": sum(stages.values()) * args.steps / dev_ms if dev_ms else None,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -54,6 +54,7 @@ enum {
 
 /* ---- library / context ------------------------------------------------------------- */
 int lwsb_version(void);                      /* 10000*major + 100*minor + patch               */
+int lwsb_has_experiments(void);              /* 1 when built with -DLWSB_EXPERIMENTS (extra kernel variants) */
 const char *lwsb_last_error(const lwsb_ctx *ctx); /* ctx may be NULL: error of the last failed
                                                 lwsb_create() on this thread                  */
 /* `stream` is a cudaStream_t to launch on (e.g. the caller's current stream) or NULL to let
@@ -143,6 +144,12 @@ int lwsb_consistency(lwsb_ctx *ctx, const void *S, int B, int M, int Nreal, cons
  * lwsb_batch / lwsb_nofuture / lwsb_online call, and how many kernels it launched. */
 int lwsb_last_compute_ms(lwsb_ctx *ctx, float *ms);
 long long lwsb_launch_count(const lwsb_ctx *ctx); /* kernels launched by this context so far */
+/* device time (ms) of each stage run since the last lwsb_load -- ms3[0] no-future sweeps, ms3[1] online chain,
+ * ms3[2] batch sweeps; -1 for a stage that did not run (lwsb_run_lws runs up to three) */
+int lwsb_last_stage_ms(lwsb_ctx *ctx, float *ms3);
+/* work of the last lwsb_batch call: out4 = {bin-iterations asked for (bins x iterations), bin-iterations of the sweeps
+ * that can move a bin (threshold below max|S|; the others are dropped before launch), work items, passes} */
+int lwsb_last_batch_work(const lwsb_ctx *ctx, long long *out4);
 /* 1 and the plan {cluster size, blocks per strip, virtual blocks, frame slots, sweeps per pass, ring rows,
  * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order, kernel variant, bins per block} (13 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it
  * ran the generic wavefront kernel */

@@ -9,7 +9,8 @@ Module attributes mirror python/lws.pyx:8-378.  There is no CPU compute path: th
 (lws_b200/liblws_b200.so, built by `python -m lws_b200.build`) and a GPU are required for
 everything that touches a spectrogram.
 """
-__version__ = "1.2.8+b200.1"
+__version__ = "1.2.8"            # the reference's (lws.pyx:8): a drop-in answers the same
+__b200_version__ = "2.0"           # this implementation's own
 __reference_version__ = "1.2.8"
 
 from .dsp import (hann, synthwin, extspec, create_weights, build_asymmetric_windows, get_thresholds)  # noqa: F401

@@ -26,6 +26,7 @@ _ci, _cd, _ll = ctypes.c_int, ctypes.c_double, ctypes.c_longlong
 # name -> (restype, argtypes): every symbol include/lws_b200.h declares
 SIGNATURES = {
     "lwsb_version": (_ci, []),
+    "lwsb_has_experiments": (_ci, []),
     "lwsb_last_error": (ctypes.c_char_p, [_vp]),
     "lwsb_create": (_ci, [_ci, _vp, _vpp]),
     "lwsb_destroy": (_ci, [_vp]),
@@ -50,6 +51,8 @@ SIGNATURES = {
     "lwsb_consistency": (_ci, [_vp, _vp, _ci, _ci, _ci, _dp, _dp, _ci, _ci, _ci, _ci, _dp]),
     "lwsb_last_compute_ms": (_ci, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "lwsb_launch_count": (_ll, [_vp]),
+    "lwsb_last_stage_ms": (_ci, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "lwsb_last_batch_work": (_ci, [_vp, ctypes.POINTER(_ll)]),
     "lwsb_last_batch_plan": (_ci, [_vp, _ip]),
     "lwsb_device_info": (_ci, [_vp, _ip, _ip, _ip, ctypes.POINTER(_ll)]),
     "lwsb_get_stats": (_ci, [_vp, _dp, _dp]),
@@ -133,6 +136,9 @@ class Context(object):
         self._h = h
         self.device = int(device)
         self._wkeys = {}
+        # a context is single-threaded (lws_b200.h): callers that share one (lws_b200.api keeps one per device) hold this
+        # lock for the whole set_weights .. store sequence
+        self.lock = threading.RLock()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -239,6 +245,18 @@ class Context(object):
                                    arrays[0].shape[1], kind, HOST, p1, n1, p2, n2, int(look_ahead), p3, n3, flags))
         return outs
 
+    def run_lws_device(self, in_ptrs, out_ptrs, T, Nreal, kind, nf_thr, on_thr, look_ahead, b_thr, flags=0):
+        """lwsb_run_lws on device buffers (CUDA pointers as ints): nothing crosses PCIe."""
+        T = np.ascontiguousarray(T, dtype=np.intc)
+        self._T, self._Nreal = T, int(Nreal)
+        t1, p1, n1 = self._thr(nf_thr)
+        t2, p2, n2 = self._thr(on_thr)
+        t3, p3, n3 = self._thr(b_thr)
+        a_in = (ctypes.c_void_p * len(in_ptrs))(*in_ptrs)
+        a_out = (ctypes.c_void_p * len(out_ptrs))(*out_ptrs)
+        self._c(lib().lwsb_run_lws(self._h, a_in, a_out, T.ctypes.data_as(_ip), len(in_ptrs), int(Nreal), kind, DEVICE,
+                                   p1, n1, p2, n2, int(look_ahead), p3, n3, flags))
+
     # -- transforms -------------------------------------------------------------------------
     def stft(self, x, awin, fsize, fshift, fftsize, perfectrec):
         """x: (B, nsamples) float64 C-contiguous -> (B, M, fftsize//2+1) complex128."""
@@ -294,6 +312,17 @@ class Context(object):
         ms = ctypes.c_float(0)
         self._c(lib().lwsb_last_compute_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
+
+    def last_stage_ms(self):
+        """device ms of the stages run since the last load: dict(nofuture=, online=, batch=), None for a stage not run"""
+        ms = (ctypes.c_float * 3)()
+        self._c(lib().lwsb_last_stage_ms(self._h, ms))
+        return {k: (float(v) if v >= 0 else None) for k, v in zip(("nofuture", "online", "batch"), ms)}
+
+    def last_batch_work(self):
+        out = (_ll * 4)()
+        self._c(lib().lwsb_last_batch_work(self._h, out))
+        return dict(zip(("bin_iters_nominal", "bin_iters_executed", "work_items", "passes"), [int(x) for x in out]))
 
     def set_tuning(self, smem_limit=0, cluster=0, sweeps_per_pass=0):
         self._c(lib().lwsb_set_tuning(self._h, int(smem_limit), int(cluster), int(sweeps_per_pass)))

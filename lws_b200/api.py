@@ -47,7 +47,13 @@ def _devices(device):
     if device is None:
         return [0]
     if isinstance(device, (list, tuple)):
-        return [int(d) for d in device]
+        devs = [int(d) for d in device]
+        if len(set(devs)) != len(devs):
+            # two shards on one device would share that device's context (resident batch, stream)
+            raise ValueError('device list contains a GPU more than once: %r' % (devs,))
+        if not devs:
+            raise ValueError('empty device list')
+        return devs
     return [int(device)]
 
 
@@ -125,33 +131,48 @@ def _check_weights(W, use_simplifications):
             'the reference\'s *fractionalQ path) are not supported by the CUDA implementation')
 
 
-def _shard(n, k):
-    """contiguous, balanced split of n utterances over k devices"""
+def _shard(frames, k):
+    """Utterance indices per device: longest-processing-time-first over the frame counts (the work of an utterance is
+    proportional to its number of frames), SURVEY.md section 8e.  Equal lengths give the contiguous balanced split.
+    Returns k' <= k non-empty index lists; the indices inside a list are in increasing order."""
+    n = len(frames)
     k = max(1, min(k, n))
-    b = [(n * i) // k for i in range(k + 1)]
-    return [(b[i], b[i + 1]) for i in range(k)]
+    if len(set(frames)) <= 1:
+        b = [(n * i) // k for i in range(k + 1)]
+        return [list(range(b[i], b[i + 1])) for i in range(k)]
+    load, parts = [0] * k, [[] for _ in range(k)]
+    for i in sorted(range(n), key=lambda i: (-frames[i], i)):
+        d = min(range(k), key=lambda d: (load[d], d))
+        parts[d].append(i)
+        load[d] += frames[i]
+    return [sorted(p) for p in parts if p]
 
 
 def _run_sharded(devices, arrs, outs, fn, overlap=False):
-    """fn(ctx, arrays, outs) on each device's contiguous share; one host thread per GPU
-    (ctypes releases the GIL, so the GPUs run concurrently)."""
-    parts = _shard(len(arrs), len(devices))
+    """fn(ctx, arrays, outs) on each device's share; one host thread per GPU (ctypes releases the GIL, so the GPUs run
+    concurrently).  A context is single-threaded (one resident batch, one stream): every use holds its lock, so host
+    threads that share a device are serialised like the reference's calls are by the GIL."""
+    parts = _shard([a.shape[0] for a in arrs], len(devices))
     slots = [0] * len(parts)
     if len(parts) == 1 and overlap and OVERLAP_MIN > 0 and len(arrs) >= OVERLAP_MIN:
         cut = (len(arrs) * 58 + 99) // 100
-        parts, devices, slots = [(0, cut), (cut, len(arrs))], [devices[0], devices[0]], [0, 1]
+        parts, devices, slots = [list(range(cut)), list(range(cut, len(arrs)))], [devices[0], devices[0]], [0, 1]
     if len(parts) == 1:
-        fn(_context(devices[0]), arrs, outs)
+        ctx = _context(devices[0])
+        with ctx.lock:
+            fn(ctx, arrs, outs)
         return
     errs = []
 
-    def work(dev, slot, lo, hi):
+    def work(dev, slot, idx):
         try:
-            fn(_context(dev, slot), arrs[lo:hi], outs[lo:hi])
+            ctx = _context(dev, slot)
+            with ctx.lock:
+                fn(ctx, [arrs[i] for i in idx], [outs[i] for i in idx])
         except BaseException as e:  # re-raised in the caller
             errs.append(e)
 
-    ts = [threading.Thread(target=work, args=(devices[i], slots[i], lo, hi)) for i, (lo, hi) in enumerate(parts)]
+    ts = [threading.Thread(target=work, args=(devices[i], slots[i], idx)) for i, idx in enumerate(parts)]
     [t.start() for t in ts]
     [t.join() for t in ts]
     if errs:
@@ -313,11 +334,12 @@ class lws(object):
         ba = get_thresholds(self.batch_iterations, self.batch_alpha, self.batch_beta, self.batch_gamma)
         xb = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
         ctx = _context(_devices(self.device)[0])
-        ctx.set_weights(_native.W, self.W)
-        ctx.set_weights(_native.W_AI, self.W_ai)
-        ctx.set_weights(_native.W_AF, self.W_af)
-        res = ctx.reconstruct(xb, self.awin, self.swin, int(self.fsize), int(self.fshift), self.perfectrec is True, nf, on,
-                              self.look_ahead, ba, consistency=return_consistency)
+        with ctx.lock:
+            ctx.set_weights(_native.W, self.W)
+            ctx.set_weights(_native.W_AI, self.W_ai)
+            ctx.set_weights(_native.W_AF, self.W_af)
+            res = ctx.reconstruct(xb, self.awin, self.swin, int(self.fsize), int(self.fshift), self.perfectrec is True, nf, on,
+                                  self.look_ahead, ba, consistency=return_consistency)
         if return_consistency:
             y, c = res
             return (y, c) if batched else (y[0], float(c[0]))

@@ -104,7 +104,14 @@ struct lwsb_ctx {
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_valid = false;
+    // per-stage device times since the last lwsb_load: 0 nofuture, 1 online, 2 batch (lwsb_last_stage_ms)
+    cudaEvent_t evs[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    bool stage_valid[3] = {false, false, false};
+    int cur_stage = -1;
     long long launches = 0;
+    // work of the last lwsb_batch call: bin-iterations asked for, bin-iterations of the sweeps that can move a bin
+    // (threshold below max|S|: the others are dropped before launch), work items, passes
+    long long last_work[4] = {0, 0, 0, 0};
 
     LwsbView view() const
     {
@@ -159,15 +166,21 @@ int upload_thresholds(lwsb_ctx *c, const double *thr, int n)
     return LWSB_OK;
 }
 
-int begin_compute(lwsb_ctx *c)
+int begin_compute(lwsb_ctx *c, int stage)
 {
     CU(c, cudaEventRecord(c->ev0, c->stream));
+    c->cur_stage = stage;
+    if (stage >= 0) CU(c, cudaEventRecord(c->evs[stage][0], c->stream));
     return LWSB_OK;
 }
 int end_compute(lwsb_ctx *c)
 {
     CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(c->ev1, c->stream));
+    if (c->cur_stage >= 0) {
+        CU(c, cudaEventRecord(c->evs[c->cur_stage][1], c->stream));
+        c->stage_valid[c->cur_stage] = true;
+    }
     c->timing_valid = true;
     return LWSB_OK;
 }
@@ -181,7 +194,16 @@ int check_resident(lwsb_ctx *c)
 } // namespace
 
 // ============================================================================ library / context
-extern "C" int lwsb_version(void) { return 100; }
+extern "C" int lwsb_version(void) { return 200; }
+
+extern "C" int lwsb_has_experiments(void)
+{
+#ifdef LWSB_EXPERIMENTS
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 extern "C" const char *lwsb_last_error(const lwsb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -211,13 +233,18 @@ extern "C" int lwsb_create(int device, void *stream, lwsb_ctx **out)
     }
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 2; ++k)
+            if ((e = cudaEventCreate(&c->evs[i][k])) != cudaSuccess) return bail("cudaEventCreate", e);
     if (const char *e1 = getenv("LWSB_STRIP_SMEM")) c->tune_smem = atoll(e1);
     if (const char *e2 = getenv("LWSB_STRIP_CLUSTER")) c->tune_cluster = atoi(e2);
     if (const char *e3 = getenv("LWSB_STRIP_SWEEPS")) c->tune_sweeps = atoi(e3);
     if (const char *e4 = getenv("LWSB_STRIP_LAG")) c->tune_lag = atoi(e4);
     if (const char *e5 = getenv("LWSB_STRIP_TM")) c->tune_tm = atoi(e5);
     if (const char *e6 = getenv("LWSB_STRIP_TRACE")) c->want_trace = atoi(e6) != 0;
+#ifdef LWSB_EXPERIMENTS
     if (const char *e7 = getenv("LWSB_STRIP_BLOCK")) c->tune_block = atoi(e7);
+#endif
     *out = c;
     return LWSB_OK;
 }
@@ -234,6 +261,9 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
     for (int i = 0; i < 3; ++i) c->raww[i].release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 2; ++k)
+            if (c->evs[i][k]) cudaEventDestroy(c->evs[i][k]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return LWSB_OK;
@@ -324,8 +354,13 @@ extern "C" int lwsb_load(lwsb_ctx *c, const void *const *S_in, const int *T, int
     if (Nreal % 2 == 0)
         return fail(c, LWSB_ERR_EVEN_NREAL, "Please only include non-negative frequencies in the input spectrogram.");
     if (!c->w[LWSB_W].valid()) return fail(c, LWSB_ERR_STATE, "set LWSB_W before loading spectrograms");
+    if (Nreal <= c->w[LWSB_W].L)
+        // extspec's mirror columns (lws.pyx:153-154) would reach outside the real bins: the reference picks up
+        // zeros / already mirrored cells there, an fsize <= 2L corner nobody uses -- refused rather than restated
+        return fail(c, LWSB_ERR_UNSUPPORTED, "spectrum narrower than the stencil reach (Nreal <= L) is not supported");
     if (int r = use_device(c)) return r;
     c->B = 0; // invalid until everything below succeeded
+    c->stage_valid[0] = c->stage_valid[1] = c->stage_valid[2] = false;
     const int Q = c->w[LWSB_W].Q, L = c->w[LWSB_W].L;
     const int Np = Nreal + 2 * L;
     const int coff = (4 - L % 4) % 4; // bin 0 lands on a 64-byte boundary
@@ -473,6 +508,8 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
         std::vector<int> items;
         const int max_pass = build_work_items(nact.data(), c->B, pl.G, items);
         const int n_items = (int)(items.size() / 2);
+        c->last_work[0] = c->total_bins * iterations; c->last_work[1] = 0; c->last_work[2] = n_items; c->last_work[3] = max_pass;
+        for (int b = 0; b < c->B; ++b) c->last_work[1] += (long long)nact[b] * c->T[b] * c->Nreal;
         const size_t done_bytes = (size_t)c->B * std::max(max_pass, 1) * STRIP_MAX_CLUSTER * sizeof(unsigned);
         if (n_items > 0) {
             CU(c, c->items.reserve(items.size() * sizeof(int)));
@@ -490,7 +527,7 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
         // One strip kernel at a time per device: its clusters wait for one another (a pass reads what the previous
         // pass of the utterance wrote), which is dead-lock free only while every cluster of the launch is resident.
         std::lock_guard<std::mutex> strip_guard(strip_mutex(c->device));
-        if (int r = begin_compute(c)) return r;
+        if (int r = begin_compute(c, 2)) return r;
         if (n_items > 0) {
             CU(c, launch_batch_strips(c->view(), c->w[LWSB_W].wr.data(), c->w[LWSB_W].wi.data(), fold,
                                       c->dthr.as<const double>(), c->max_amp.as<const double>(), iterations, pl,
@@ -510,7 +547,8 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
         }
         return LWSB_OK;
     }
-    if (int r = begin_compute(c)) return r;
+    c->last_work[0] = c->last_work[1] = c->total_bins * iterations; c->last_work[2] = c->B; c->last_work[3] = 1;
+    if (int r = begin_compute(c, 2)) return r;
     launch_sweeps_generic(c->view(), c->devw(LWSB_W), fold, c->Q, 1, c->dthr.as<const double>(), iterations, c->stream);
     c->launches += 1;
     c->last_kernel = 0;
@@ -529,7 +567,7 @@ extern "C" int lwsb_nofuture(lwsb_ctx *c, int which, const double *thresholds, i
     if (int r = use_device(c)) return r;
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
     const int fold = fold_for(c->Q, flags);
-    if (int r = begin_compute(c)) return r;
+    if (int r = begin_compute(c, 0)) return r;
     if (fold == LWSB_FOLD_Q4) // NoFuture_LWSQ4, reproduced as written (lwslib.cpp:538-617)
         launch_nofuture_q4(c->view(), c->devw(which), c->dthr.as<const double>(), iterations, c->stream);
     else
@@ -553,7 +591,7 @@ extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations
     if (int r = use_device(c)) return r;
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
     const LwsbW w3[3] = {c->devw(LWSB_W), c->devw(LWSB_W_AI), c->devw(LWSB_W_AF)};
-    if (int r = begin_compute(c)) return r;
+    if (int r = begin_compute(c, 1)) return r;
     bool ring = false;
     if (!(flags & LWSB_FORCE_GENERIC)) {
         cudaError_t e = cudaSuccess;
@@ -910,6 +948,27 @@ extern "C" int lwsb_last_compute_ms(lwsb_ctx *c, float *ms)
 
 extern "C" long long lwsb_launch_count(const lwsb_ctx *c) { return c ? c->launches : 0; }
 
+extern "C" int lwsb_last_stage_ms(lwsb_ctx *c, float *ms3)
+{
+    CHECK_CTX(c);
+    if (!ms3) return fail(c, LWSB_ERR_ARG, "ms3 is NULL");
+    if (int r = use_device(c)) return r;
+    for (int i = 0; i < 3; ++i) {
+        ms3[i] = -1.0f;
+        if (!c->stage_valid[i]) continue;
+        CU(c, cudaEventSynchronize(c->evs[i][1]));
+        CU(c, cudaEventElapsedTime(&ms3[i], c->evs[i][0], c->evs[i][1]));
+    }
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_last_batch_work(const lwsb_ctx *c, long long *out4)
+{
+    if (!c || !out4) return LWSB_ERR_ARG;
+    for (int i = 0; i < 4; ++i) out4[i] = c->last_work[i];
+    return LWSB_OK;
+}
+
 extern "C" int lwsb_last_batch_cycles(lwsb_ctx *c, unsigned long long *out7)
 {
     CHECK_CTX(c);
@@ -962,6 +1021,9 @@ extern "C" int lwsb_set_block_bins(lwsb_ctx *c, int bins)
 {
     CHECK_CTX(c);
     if (bins != 0 && bins != 4 && bins != 8) return fail(c, LWSB_ERR_ARG, "bins per block: 0 (automatic), 4 or 8");
+#ifndef LWSB_EXPERIMENTS
+    if (bins == 4) return fail(c, LWSB_ERR_UNSUPPORTED, "4-bin blocks are built only with -DLWSB_EXPERIMENTS");
+#endif
     c->tune_block = bins;
     return LWSB_OK;
 }
@@ -969,7 +1031,7 @@ extern "C" int lwsb_set_block_bins(lwsb_ctx *c, int bins)
 extern "C" int lwsb_set_variant(lwsb_ctx *c, int sweep_lag, int tensor_memory)
 {
     CHECK_CTX(c);
-    if (sweep_lag < 0 || tensor_memory < 0 || (tensor_memory > LWSB_VARIANT_SCALAR && (tensor_memory < LWSB_VARIANT_PAIR || tensor_memory > LWSB_VARIANT_PAIR + 5)))
+    if (sweep_lag < 0 || tensor_memory < 0 || (tensor_memory > LWSB_VARIANT_DUO && (tensor_memory < LWSB_VARIANT_PAIR || tensor_memory > LWSB_VARIANT_PAIR + 5)))
         return fail(c, LWSB_ERR_ARG, "bad variant values");
     c->tune_lag = sweep_lag; c->tune_tm = tensor_memory;
     return LWSB_OK;

@@ -192,11 +192,13 @@ constexpr int SBK = 8, LAGB = 2;
 constexpr bool HAS_TM = true;
 #include "strip_body.inc"
 } // namespace bk8
+#ifdef LWSB_EXPERIMENTS
 namespace bk4 {
 constexpr int SBK = 4, LAGB = 3;
 constexpr bool HAS_TM = false;
 #include "strip_body.inc"
 } // namespace bk4
+#endif
 
 // ---------------------------------------------------------------- self-check of the branch-free sqrt / division
 // Inputs: a 64-bit mix of the index (every exponent from 2^-1022 to 2^1023 and signs on the numerator); counts
@@ -245,6 +247,10 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
     // automatic = one thread per task: with the branch-free projection it is as fast as or faster than the pair-split
     // kernels on every plan measured; those stay selectable
     if (var == LWSB_VARIANT_AUTO) var = LWSB_VARIANT_SCALAR;
+    if (var == LWSB_VARIANT_DUO && !pair_ok) var = LWSB_VARIANT_SCALAR; // two lanes per task: the folded Q = 2 / Q = 4 updates
+#ifndef LWSB_EXPERIMENTS
+    if (var == LWSB_VARIANT_TM || var >= LWSB_VARIANT_PAIR) var = LWSB_VARIANT_SCALAR;
+#endif
     if (var >= LWSB_VARIANT_PAIR && (!pair_ok || var > LWSB_VARIANT_PAIR + 5)) var = LWSB_VARIANT_SCALAR;
 #ifndef LWSB_PAIR_EXPERIMENTS
     if (var >= LWSB_VARIANT_PAIR) var = LWSB_VARIANT_PAIR + LWSB_PAIR_DEFAULT_MODE;
@@ -252,7 +258,8 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
     if (var == LWSB_VARIANT_TM && Q > 4) var = LWSB_VARIANT_SCALAR;
     const bool tm = var == LWSB_VARIANT_TM;
     const bool pair = var >= LWSB_VARIANT_PAIR;
-    const int task_cap = tm ? 128 : (pair ? (pair_thread_cap(max_sweeps) - 32) / 2 : 256 - 32);
+    const bool duo = var == LWSB_VARIANT_DUO;
+    const int task_cap = tm ? 128 : (duo ? 7 * 32 : (pair ? (pair_thread_cap(max_sweeps) - 32) / 2 : 256 - 32)); // DUO: 14 named barriers = 7 warp pairs
     bool found = false;
     double best = 0.0;
     // block size: 8 bins with frames 2 blocks apart, or (Q <= 4, not the tensor-memory variant) 4 bins with frames 3
@@ -330,9 +337,9 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                     found = true; best = cost;
                     out->SBK = SBK; out->LAGB = LAGB;
                     out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast;
-                    out->TM = tm ? LWSB_VARIANT_TM : (pair ? var : 0);
+                    out->TM = tm ? LWSB_VARIANT_TM : (pair ? var : (duo ? LWSB_VARIANT_DUO : 0));
                     out->R = QS * (G - 1) + 2 * Q + SLEAD + NS;
-                    out->nthreads = ((pair ? 2 : 1) * NS * G + 31) / 32 * 32 + 32;
+                    out->nthreads = duo ? 2 * ((NS * G + 31) / 32 * 32) + 32 : ((pair ? 2 : 1) * NS * G + 31) / 32 * 32 + 32;
                     out->smem_bytes = (int)(fixed + (size_t)out->R * (rowbytes + 8));
                     out->smem_limit = (int)smem_limit;
                 }
@@ -360,10 +367,12 @@ cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const 
     prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch; prm.QS = pl.QS; prm.GFAST = pl.GFAST;
     prm.status = status;
     if (pl.SBK == 4) {
+#ifdef LWSB_EXPERIMENTS
         switch (v.Q) {
         case 2: return bk4::launch_strips_q<2>(prm, wr_host, wi_host, fold, pl, v.B, s);
         case 4: return bk4::launch_strips_q<4>(prm, wr_host, wi_host, fold, pl, v.B, s);
         }
+#endif
         return cudaErrorInvalidValue;
     }
     switch (v.Q) {

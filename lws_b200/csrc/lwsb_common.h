@@ -18,9 +18,10 @@
 
 // Formula family of the reference's C variants (how the +k / -k neighbours share a weight).
 enum { LWSB_FOLD_ANY = 0, LWSB_FOLD_Q2 = 2, LWSB_FOLD_Q4 = 4, LWSB_FOLD_NF4 = 5 };
-// variants of the cluster strip kernel (StripPlan::TM, lwsb_set_variant): one thread per task, tensor-memory
-// producer / consumer warps, or two lanes per task (LWSB_VARIANT_PAIR + register-window mode 0..2)
-enum { LWSB_VARIANT_AUTO = 0, LWSB_VARIANT_TM = 1, LWSB_VARIANT_SCALAR = 2, LWSB_VARIANT_PAIR = 10 };
+// variants of the cluster strip kernel (StripPlan::TM, lwsb_set_variant): one thread per task (SCALAR), two lanes per
+// task alternating bins (DUO); builds with -DLWSB_EXPERIMENTS also have the tensor-memory producer / consumer warps (TM)
+// and two lanes per task split by component (LWSB_VARIANT_PAIR + register-window mode 0..2)
+enum { LWSB_VARIANT_AUTO = 0, LWSB_VARIANT_TM = 1, LWSB_VARIANT_SCALAR = 2, LWSB_VARIANT_DUO = 3, LWSB_VARIANT_PAIR = 10 };
 
 // One term of the linear stencil   acc += (cr + i*ci) * E[m + dr][e + dk].
 // For LWSB_FOLD_NF4 (the reference's NoFuture_LWSQ4 with its doubled bin offset) dk is

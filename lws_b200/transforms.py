@@ -33,7 +33,9 @@ def stft(x, fsize, fshift, awin, fftsize=None, perfectrec=False, *, device=None)
     if np.iscomplexobj(x):
         raise TypeError('real signals only')
     xb = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
-    S = _ctx(device).stft(xb, awin, int(fsize), int(fshift), int(fftsize), perfectrec is True)
+    ctx = _ctx(device)
+    with ctx.lock:
+        S = ctx.stft(xb, awin, int(fsize), int(fshift), int(fftsize), perfectrec is True)
     return S if batched else S[0]
 
 
@@ -55,7 +57,9 @@ def istft(spec, fshift, swin, awin=None, fftsize=None, perfectrec=False, *, devi
     if len(swin) > fsize:
         raise ValueError('operands could not be broadcast together: frame (%d,) window %s' % (fsize, swin.shape))
     Sb = np.ascontiguousarray(spec if batched else spec[None], dtype=np.complex128)
-    sig = _ctx(device).istft(Sb, swin, int(fshift))
+    ctx = _ctx(device)
+    with ctx.lock:
+        sig = ctx.istft(Sb, swin, int(fshift))
     if perfectrec is True:
         residual_size = fsize % fshift
         pre_pad_length = fsize - fshift if residual_size == 0 else fsize - residual_size
@@ -78,5 +82,7 @@ def get_consistency(S, fsize, fshift, awin, swin, perfectrec=False, *, device=No
     awin = np.squeeze(np.asarray(awin, dtype=np.float64))
     swin = np.squeeze(np.asarray(swin, dtype=np.float64))
     Sb = np.ascontiguousarray(S if batched else S[None], dtype=np.complex128)
-    c = _ctx(device).consistency(Sb, awin, swin, int(fshift), perfectrec is True)
+    ctx = _ctx(device)
+    with ctx.lock:
+        c = ctx.consistency(Sb, awin, swin, int(fshift), perfectrec is True)
     return c if batched else float(c[0])

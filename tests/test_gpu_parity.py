@@ -31,6 +31,15 @@ def gpu():
     return lws_b200
 
 
+def _experiments():
+    from lws_b200 import _native
+    return _native.lib().lwsb_has_experiments() == 1
+
+
+needs_experiments = pytest.mark.skipif("not __import__('lws_b200')._native.lib().lwsb_has_experiments()",
+                                       reason="kernel variants built only with -DLWSB_EXPERIMENTS (LWSB_NVCC_EXTRA)")
+
+
 def _ctor(mod, case, **extra):
     kw = dict(case["kwargs"])
     kw.update(extra)
@@ -297,6 +306,61 @@ def test_strip_kernel_ragged_batch_persistent_clusters(gpu, oracle):
         ctx.set_tuning(0, 0, 0)
 
 
+DUO_CASES = [  # fsize, hop, samples, iterations, cluster, sweeps per pass, sweep lag: many warp pairs, every register tier
+    (1024, 256, 60000, 30, 2, 7, 0), (1024, 256, 60000, 30, 2, 6, 5), (1024, 256, 60000, 40, 4, 16, 0), (1024, 256, 60000, 40, 4, 20, 0),
+    (1024, 256, 60000, 40, 4, 24, 0), (1024, 256, 60000, 40, 8, 32, 0), (512, 128, 32000, 100, 0, 0, 0), (128, 64, 9000, 30, 1, 0, 0),
+    (512, 128, 700, 5, 1, 0, 0),
+]
+
+
+@pytest.mark.parametrize("fs,hop,n,its,cluster,sweeps,lag", DUO_CASES, ids=["%d-%d-n%d-it%d-C%d-G%d-lag%d" % c for c in DUO_CASES])
+def test_strip_kernel_two_lanes_per_task(gpu, oracle, fs, hop, n, its, cluster, sweeps, lag):
+    """The two-lanes-per-task kernel (lane l of warp w takes the even bins of a block, lane l of warp w + NWT the odd
+    ones, a named barrier per hand-over) at plans with 2-7 warp pairs: identical bits to the oracle."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(fs, hop), gpu.lws(fs, hop)
+    A = np.abs(po.stft(make_signal("tonal", 3, n)))
+    try:
+        ctx.set_tuning(0, cluster, sweeps)
+        ctx.set_variant(lag, 3)
+        for thr in (np.zeros(its), gpu.get_thresholds(its, 100 if its > 50 else 2.0, 0.1, 1)):
+            Y = pg.batch_lws(A, thresholds=thr)
+            plan = ctx.last_batch_plan()
+            assert plan is not None and plan["tensor_memory"] == 3, plan
+            assert cluster == 0 or plan["cluster"] == cluster
+            _close(Y, po.batch_lws(A, thresholds=thr), "two lanes per task %s" % (plan,))
+    finally:
+        ctx.set_tuning(0, 0, 0)
+        ctx.set_variant(0, 0)
+
+
+def test_cfg5_plan_vs_oracle(gpu, oracle):
+    """BASELINE configs[4] as planned for 4 utterances per GPU (Q = 8 LWSanyQ, cluster of 8 strips, >= 3 passes of the
+    sweeps the ring holds, 200 default sweeps) on 1/16 of the frames (T = 352), 4 utterances, against the oracle."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(2048, 256), gpu.lws(2048, 256)
+    x = make_signal("tonal", 5005, 90112 - 2048 + 256)
+    A = np.abs(po.stft(x))
+    assert A.shape == (352, 1025), A.shape
+    thr = gpu.get_thresholds(200, 100, 0.1, 1)
+    As = [A, A[::-1].copy(), np.abs(po.stft(make_signal("white", 5006, 90112 - 2048 + 256))), A]
+    try:
+        ctx.set_tuning(0, 8, 0)
+        Ys = pg.batch_lws(As, thresholds=thr)
+        plan = ctx.last_batch_plan()
+        work = ctx.last_batch_work()
+        assert plan is not None and plan["cluster"] == 8 and plan["sweeps_per_pass"] >= 7, plan
+        assert work["passes"] >= 3, (plan, work)
+    finally:
+        ctx.set_tuning(0, 0, 0)
+    want = po.batch_lws(A, thresholds=thr)
+    _close(Ys[0], want, "cfg5 plan %s" % (plan,))
+    assert np.array_equal(Ys[3], Ys[0])
+    _close(Ys[2], po.batch_lws(As[2], thresholds=thr), "cfg5 plan, white utterance")
+
+
 def test_generic_and_strip_kernels_agree(gpu):
     from lws_b200 import _native
     p = gpu.lws(1024, 256)
@@ -307,6 +371,7 @@ def test_generic_and_strip_kernels_agree(gpu):
     assert np.array_equal(a, b)
 
 
+@needs_experiments
 @pytest.mark.parametrize("fs,hop,n,its,cluster,lag", [(512, 128, 9000, 9, 2, 0), (512, 128, 9000, 9, 4, 5), (1024, 256, 30000, 12, 8, 0),
                                                       (128, 64, 9000, 10, 1, 0), (128, 64, 9000, 10, 2, 3)])
 def test_strip_kernel_tensor_memory_variant(gpu, oracle, fs, hop, n, its, cluster, lag):
@@ -334,12 +399,15 @@ PAIR_CASES = [(512, 128, 9000, 9, 2, 0), (512, 128, 9000, 9, 4, 5), (1024, 256, 
               (128, 64, 9000, 10, 1, 0), (128, 64, 9000, 10, 2, 3), (512, 128, 700, 5, 1, 0)]
 
 
-@pytest.mark.parametrize("variant", [2, 10, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("variant", [2, 3, 10, 11, 12, 13, 14, 15])
 @pytest.mark.parametrize("fs,hop,n,its,cluster,lag", PAIR_CASES)
 def test_strip_kernel_variants(gpu, oracle, variant, fs, hop, n, its, cluster, lag):
-    """One thread per task (2) and the pair-split kernels (10 + window mode + 3 * explicit pipelining; modes that are
-    not compiled into this build fall back to the default one): same bits, default and custom windows."""
+    """One thread per task (2), two lanes per task alternating bins (3) and -- experimental builds -- the pair-split
+    kernels (10 + window mode + 3 * explicit pipelining; modes that are not compiled into this build fall back to the
+    default one): same bits, default and custom windows."""
     from lws_b200 import api
+    if variant >= 10 and not _experiments():
+        pytest.skip("pair-split kernels are built only with -DLWSB_EXPERIMENTS")
     ctx = api._context(0)
     po, pg = oracle.lws(fs, hop), gpu.lws(fs, hop)
     A = np.abs(po.stft(make_signal("tonal", 4, n)))
@@ -351,7 +419,8 @@ def test_strip_kernel_variants(gpu, oracle, variant, fs, hop, n, its, cluster, l
             plan = ctx.last_batch_plan()
             assert plan is not None and plan["cluster"] == cluster
             assert (plan["tensor_memory"] == 0) == (variant == 2), plan
-            assert plan["threads"] <= 256
+            assert plan["tensor_memory"] == variant or variant >= 10, plan
+            assert plan["threads"] <= (480 if variant == 3 else 256)
             assert lag == 0 or plan["sweep_lag"] == lag
             _close(Y, po.batch_lws(A, thresholds=thr), "variant %d %s" % (variant, plan))
     finally:
@@ -359,10 +428,12 @@ def test_strip_kernel_variants(gpu, oracle, variant, fs, hop, n, its, cluster, l
         ctx.set_variant(0, 0)
 
 
-@pytest.mark.parametrize("variant", [2, 13, 14])
+@pytest.mark.parametrize("variant", [2, 3, 13, 14])
 def test_strip_kernel_variants_custom_window_and_complex_input(gpu, oracle, variant):
     """A window whose |W| > 1e-12 mask differs from the default pattern (run-time mask path) and a complex input."""
     from lws_b200 import api
+    if variant >= 10 and not _experiments():
+        pytest.skip("pair-split kernels are built only with -DLWSB_EXPERIMENTS")
     ctx = api._context(0)
     g = golden("custom_win")
     case = [c for c in CASES if c["name"] == "custom_win"][0]
@@ -397,6 +468,7 @@ BLOCK4_CASES = [  # fsize, hop, samples, iterations, cluster, sweeps per pass, v
 ]
 
 
+@needs_experiments
 @pytest.mark.parametrize("fs,hop,n,its,cluster,sweeps,variant", BLOCK4_CASES, ids=["%d-%d-n%d-it%d-C%d-G%d-V%d" % c for c in BLOCK4_CASES])
 def test_strip_kernel_four_bin_blocks(gpu, oracle, fs, hop, n, its, cluster, sweeps, variant):
     """4 bins per block, frames 3 blocks apart (the L = 5 halo bins of a strip span two blocks): same bits."""
@@ -420,6 +492,7 @@ def test_strip_kernel_four_bin_blocks(gpu, oracle, fs, hop, n, its, cluster, swe
         ctx.set_variant(0, 0)
 
 
+@needs_experiments
 def test_strip_kernel_four_bin_blocks_ragged_batch(gpu, oracle):
     from lws_b200 import api
     ctx = api._context(0)

@@ -28,11 +28,40 @@ def test_reference_arm_only_rank0_prints(tmp_path):
 
 
 def test_api_sharding_is_a_partition():
+    """equal lengths: contiguous, balanced split (BASELINE configs[3]: 256 over 8 -> 32 per GPU; configs[4]: 32 -> 4)"""
     from lws_b200 import api
-    for n in (1, 2, 7, 64, 65, 256):
+    for n in (1, 2, 7, 32, 64, 65, 256):
         for k in (1, 2, 4, 8):
-            parts = api._shard(n, k)
-            assert parts[0][0] == 0 and parts[-1][1] == n
-            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
-            sizes = [hi - lo for lo, hi in parts]
+            parts = api._shard([628] * n, k)
+            assert sorted(i for p in parts for i in p) == list(range(n))
+            assert all(p == list(range(p[0], p[-1] + 1)) for p in parts)
+            sizes = [len(p) for p in parts]
             assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1 and len(parts) == min(n, k)
+    assert [len(p) for p in api._shard([628] * 256, 8)] == [32] * 8
+    assert [len(p) for p in api._shard([5632] * 32, 8)] == [4] * 8
+
+
+def test_api_sharding_balances_ragged_batches_by_frames():
+    """ragged lengths: longest-processing-time-first over the frame counts -- the busiest device
+    carries at most 4/3 - 1/(3k) of the optimum (Graham's bound), far better than the split by count"""
+    from lws_b200 import api
+    rng = np.random.default_rng(8)
+    for n, k in ((9, 2), (40, 4), (100, 8), (17, 8), (3, 8)):
+        frames = [int(f) for f in rng.integers(20, 3000, n)]
+        frames[0] = 9000  # one long utterance
+        parts = api._shard(frames, k)
+        assert sorted(i for p in parts for i in p) == list(range(n)) and all(p == sorted(p) for p in parts)
+        loads = [sum(frames[i] for i in p) for p in parts]
+        lower = max(max(frames), -(-sum(frames) // min(k, n)))
+        assert max(loads) <= lower * (4.0 / 3.0) + 1, (loads, lower)
+        by_count = [(n * i) // min(k, n) for i in range(min(k, n) + 1)]
+        naive = max(sum(frames[a:b]) for a, b in zip(by_count, by_count[1:]))
+        assert max(loads) <= naive
+
+
+def test_api_rejects_duplicate_devices():
+    from lws_b200 import api
+    import pytest
+    with pytest.raises(ValueError):
+        api._devices([0, 0])
+    assert api._devices([1, 0]) == [1, 0] and api._devices(None) == [0] and api._devices(3) == [3]
