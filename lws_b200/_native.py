@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblws_b200.so")
+LIB_PATH = os.environ.get("LWSB_LIB_PATH") or os.path.join(_HERE, "liblws_b200.so")  # the override is for timing experiments with instrumented builds
 
 C128, F64 = 0, 1
 W, W_AI, W_AF = 0, 1, 2

@@ -10,7 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "liblws_b200.so")
+LIB = os.environ.get("LWSB_LIB_PATH") or os.path.join(HERE, "liblws_b200.so")
 SOURCES = ["api.cu", "kernels_generic.cu", "kernels_batch.cu", "kernels_online.cu", "kernels_fft.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("LWSB_NVCC_EXTRA", "").split()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, os.environ.get("LWSB_OBJDIR", "build"))
     os.makedirs(objdir, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     compile_flags = [f for f in NVCC_FLAGS if f not in ("--shared",)]

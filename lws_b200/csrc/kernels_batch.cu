@@ -280,38 +280,52 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
         if (NBr < 2 || SBK * NBr < 2 * SL) continue;
         // every strip needs real bins and the last one the whole upper mirror zone
         if ((C - 1) * NBr * SBK > Nreal - 1 - SL) continue;
-        int pitch = SBK * NBr + 2 * SL;
-        if ((pitch & 1) == 0) ++pitch; // odd pitch: conflict-free 128-bit accesses across a warp's rows
+        // ring row: the strip's bins, an L-bin halo on either side and 7 cells of slack (the row starts (frame - slot *
+        // pitch) mod 8 cells into its slot, see ring_off in strip_body.inc)
+        const int pitch = SBK * NBr + 2 * SL + 7;
         const size_t rowbytes = (size_t)pitch * 16;
         const size_t fixed = 64 + 16 + (size_t)(iters + 8) * sizeof(int) + 256 + 256; // flags, sweep list, alignment, static shared memory of the kernel
         if (smem_limit < fixed + rowbytes * 8) continue;
         const int Rmax = (int)((smem_limit - fixed) / (rowbytes + 8));
         const int ncl = std::max(1, (sm_count * 9 / 10) / C); // GPC packing loses a few SMs to clusters
-        // sweep lag: Q frames is the minimum; an odd lag lets the sweep-fastest thread order be bank-conflict free
+        // sweep lag: Q frames is the minimum; an odd lag makes the sweep-fastest thread order bank-conflict free
         for (int QS = Q; QS <= Q + 1; ++QS) {
             if (Rmax < 2 * Q + SLEAD + NS) continue;
             int Gmax = (Rmax - 2 * Q - SLEAD - NS) / QS + 1;
-            Gmax = std::min(Gmax, task_cap / NS);
             Gmax = std::min(Gmax, iters);
             if (max_sweeps > 0) Gmax = std::min(Gmax, max_sweeps);
             if (max_sweeps < -1) Gmax = std::min(Gmax, -max_sweeps); // experiments: negative = sweeps per pass without the pair kernels' thread cap
             for (int G = Gmax; G >= 1; --G) {
-                // shared-memory wavefronts per warp access: 8 tasks (a quarter-warp of 128-bit accesses, or a
-                // half-warp of lane pairs reading 64 bits each) hit 16-byte bank groups (j - QS*g) mod 8 (odd
-                // pitch); the busiest group sets the count
-                double f = 0.0; int gfast = 0;
+                // Shared-memory cycles per 128-bit warp access (measured, tools/ubench/lds.cu): the 16 lanes of a half-warp
+                // are served together, one cycle per round of distinct 16-byte cells in different bank groups -- 2 cycles
+                // when the 16 cells spread evenly over the 8 groups, more when a group is hit 3 times or more.  A lane's
+                // bank group is (frame + column) mod 8 (ring_off) and the lanes of a warp are on the same column mod 8, so
+                // what counts is the frames' residues.  Two thread orders:
+                //   frame-fastest: lanes on consecutive frame slots (compact, but a half-warp that straddles the newest /
+                //     oldest frame in flight or two sweeps hits a group three times);
+                //   sweep-fastest: the sweeps of a frame slot padded to groups of 8 lanes, QS frames apart: with an odd
+                //     QS each group covers 8 different residues whatever the slots' frames are -- conflict free.
+                double f = 0.0; int gfast = 0, lanes_best = 0;
                 for (int order = 0; order < 2; ++order) {
-                    double waves = 0.0; int quarters = 0;
-                    for (int q0 = 0; q0 < NS * G; q0 += 8) {
-                        int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
-                        for (int tid = q0; tid < q0 + 8 && tid < NS * G; ++tid) {
-                            const int jj = order ? tid / G : tid % NS, gg = order ? tid % G : tid / NS;
-                            mx = std::max(mx, ++cnt[((jj - QS * gg) % 8 + 8) % 8]);
+                    const int GP8 = (G + 7) & ~7;
+                    const int lanes = order ? NS * GP8 : NS * G;
+                    if (lanes > task_cap) continue;
+                    double cyc = 0.0, ideal = 0.0;
+                    for (int ph = 0; ph < NS; ++ph)       // slots 0 .. ph have wrapped to their next frame (+NS)
+                        for (int h0 = 0; h0 < lanes; h0 += 16) {
+                            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0, act = 0;
+                            for (int l = h0; l < h0 + 16 && l < lanes; ++l) {
+                                const int jj = order ? l / GP8 : l % NS, gg = order ? l % GP8 : l / NS;
+                                if (gg >= G) continue;
+                                const int fr = jj + (jj <= ph ? NS : 0) - QS * gg;
+                                mx = std::max(mx, ++cnt[((fr % 8) + 8) % 8]); ++act;
+                            }
+                            cyc += mx; ideal += (act + 7) / 8;
                         }
-                        waves += mx; ++quarters;
-                    }
-                    if (order == 0 || waves / quarters < f) { f = waves / quarters; gfast = order; }
+                    const double ff = ideal > 0.0 ? cyc / ideal : 1.0;
+                    if (lanes_best == 0 || ff < f) { f = ff; gfast = order; lanes_best = lanes; }
                 }
+                if (lanes_best == 0) continue;
                 if (force_lag > 0 && QS != force_lag) continue;
                 const int npass = (iters + G - 1) / G;
                 const double steps = (double)LAGB * (maxT + QS * G) + NBV + (C - 1) * NBr;
@@ -321,7 +335,7 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                 // pipe saturates); measured over cluster sizes 2-8, 2-6 warps, conflict factors 1.0-1.75: 11.5k-19.5k cycles.
                 // The stream scales with the bins of a block, the two CTA barriers do not.
                 // Pair-split: half the instructions per warp and twice the warps.  A pass adds a fixed prologue.
-                const int cwarps = ((pair ? 2 : 1) * NS * G + 31) / 32;
+                const int cwarps = ((pair || duo ? 2 : 1) * lanes_best + 31) / 32;
                 // per-warp cost scales with the terms per bin: 6 (Q = 2), 17 (Q = 4, folded), 74 (Q = 8)
                 const double tscale = Q == 2 ? 0.4 : (Q == 4 ? 1.0 : 10.0); // Q = 8: 74 unfolded terms, block update not software-pipelined (measured 136k cycles per macro-step)
                 const double bscale = SBK / 8.0;
@@ -339,7 +353,7 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                     out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast;
                     out->TM = tm ? LWSB_VARIANT_TM : (pair ? var : (duo ? LWSB_VARIANT_DUO : 0));
                     out->R = QS * (G - 1) + 2 * Q + SLEAD + NS;
-                    out->nthreads = duo ? 2 * ((NS * G + 31) / 32 * 32) + 32 : ((pair ? 2 : 1) * NS * G + 31) / 32 * 32 + 32;
+                    out->nthreads = duo ? 2 * ((lanes_best + 31) / 32 * 32) : ((pair ? 2 : 1) * lanes_best + 31) / 32 * 32 + 32;
                     out->smem_bytes = (int)(fixed + (size_t)out->R * (rowbytes + 8));
                     out->smem_limit = (int)smem_limit;
                 }

@@ -419,7 +419,7 @@ def test_strip_kernel_variants(gpu, oracle, variant, fs, hop, n, its, cluster, l
             plan = ctx.last_batch_plan()
             assert plan is not None and plan["cluster"] == cluster
             assert (plan["tensor_memory"] == 0) == (variant == 2), plan
-            assert plan["tensor_memory"] == variant or variant >= 10, plan
+            assert variant >= 10 or plan["tensor_memory"] == {2: 0, 3: 3}[variant], plan
             assert plan["threads"] <= (480 if variant == 3 else 256)
             assert lag == 0 or plan["sweep_lag"] == lag
             _close(Y, po.batch_lws(A, thresholds=thr), "variant %d %s" % (variant, plan))
