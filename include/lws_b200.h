@@ -150,6 +150,9 @@ int lwsb_last_stage_ms(lwsb_ctx *ctx, float *ms3);
 /* work of the last lwsb_batch call: out4 = {bin-iterations asked for (bins x iterations), bin-iterations of the sweeps
  * that can move a bin (threshold below max|S|; the others are dropped before launch), work items, passes} */
 int lwsb_last_batch_work(const lwsb_ctx *ctx, long long *out4);
+/* which kernel the last lwsb_online call ran: 0 generic (global memory), 1 shared-memory ring with one bin per step,
+ * 2 ring with two bins per step */
+int lwsb_last_online_kernel(const lwsb_ctx *ctx);
 /* 1 and the plan {cluster size, blocks per strip, virtual blocks, frame slots, sweeps per pass, ring rows,
  * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order, kernel variant, bins per block} (13 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it
  * ran the generic wavefront kernel */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "lwsb_launch_count": (_ll, [_vp]),
     "lwsb_last_stage_ms": (_ci, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "lwsb_last_batch_work": (_ci, [_vp, ctypes.POINTER(_ll)]),
+    "lwsb_last_online_kernel": (_ci, [_vp]),
     "lwsb_last_batch_plan": (_ci, [_vp, _ip]),
     "lwsb_device_info": (_ci, [_vp, _ip, _ip, _ip, ctypes.POINTER(_ll)]),
     "lwsb_get_stats": (_ci, [_vp, _dp, _dp]),
@@ -318,6 +319,9 @@ class Context(object):
         ms = (ctypes.c_float * 3)()
         self._c(lib().lwsb_last_stage_ms(self._h, ms))
         return {k: (float(v) if v >= 0 else None) for k, v in zip(("nofuture", "online", "batch"), ms)}
+
+    def last_online_kernel(self):
+        return int(lib().lwsb_last_online_kernel(self._h))
 
     def last_batch_work(self):
         out = (_ll * 4)()

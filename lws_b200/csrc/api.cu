@@ -92,6 +92,7 @@ struct lwsb_ctx {
     int trace_items = 0;
     std::vector<int> trace_list;
     int last_kernel = 0;                   // 0 generic, 1 strips (introspection)
+    int last_online_kernel = 0;            // 0 generic, 1 ring (one bin per step), 2 ring (two bins per step)
     long long tune_smem = 0;               // tuning knobs (lwsb_set_tuning): shared-memory budget, cluster size,
     int tune_cluster = 0, tune_sweeps = 0; // sweeps per pass; 0 = automatic
     int tune_block = 0;                    // bins per block of the strip kernel: 0 automatic, 4 or 8 (env LWSB_STRIP_BLOCK, lwsb_set_block_bins)
@@ -593,6 +594,7 @@ extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations
     const LwsbW w3[3] = {c->devw(LWSB_W), c->devw(LWSB_W_AI), c->devw(LWSB_W_AF)};
     if (int r = begin_compute(c, 1)) return r;
     bool ring = false;
+    c->last_online_kernel = 0;
     if (!(flags & LWSB_FORCE_GENERIC)) {
         cudaError_t e = cudaSuccess;
         CU(c, c->status.reserve(256));
@@ -601,7 +603,7 @@ extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations
         const double *wih[3] = {c->w[0].wi.data(), c->w[1].wi.data(), c->w[2].wi.data()};
         ring = launch_online_ring(c->view(), wrh, wih, fold_for(c->Q, flags), c->dthr.as<const double>(), iterations,
                                   look_ahead, c->T.data(), c->prop.sharedMemPerBlockOptin, c->status.as<unsigned>(),
-                                  c->stream, &e);
+                                  c->stream, &e, &c->last_online_kernel);
         CU(c, e);
     }
     if (!ring)
@@ -613,7 +615,11 @@ extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations
         unsigned st = 0;
         CU(c, cudaMemcpyAsync(&st, c->status.p, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
-        if (st != 0) return fail(c, LWSB_ERR_CUDA, "online kernel: shared-memory ring undersized (internal error)");
+        if (st != 0) {
+            char msg[112];
+            snprintf(msg, sizeof msg, "online kernel: internal schedule error (code 0x%x): results are invalid", st);
+            return fail(c, LWSB_ERR_CUDA, msg);
+        }
     }
     return LWSB_OK;
 }
@@ -961,6 +967,8 @@ extern "C" int lwsb_last_stage_ms(lwsb_ctx *c, float *ms3)
     }
     return LWSB_OK;
 }
+
+extern "C" int lwsb_last_online_kernel(const lwsb_ctx *c) { return c ? c->last_online_kernel : LWSB_ERR_ARG; }
 
 extern "C" int lwsb_last_batch_work(const lwsb_ctx *c, long long *out4)
 {

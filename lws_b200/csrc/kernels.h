@@ -30,7 +30,7 @@ void launch_online_generic(const LwsbView &v, const LwsbW *w3, int fold, const d
 // kernels_online.cu
 bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const double *const *wi_host, int fold,
                         const double *thr, int iters, int LA, const int *T_host, size_t smem_limit, unsigned *status,
-                        cudaStream_t s, cudaError_t *err);
+                        cudaStream_t s, cudaError_t *err, int *which_kernel);
 void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, int iters, cudaStream_t s);
 
 // kernels_batch.cu

@@ -440,10 +440,12 @@ int online_max_span(int T, int Nreal, int S, int Q, int iters, int LA)
 
 template <int Q, int FOLD>
 cudaError_t launch_t(const LwsbView &v, const OnlineW<Q> &w, const double *thr, int iters, int LA, int R, int pitch, int S, int nt,
-                     size_t bytes, unsigned *status, cudaStream_t s)
+                     size_t bytes, unsigned *status, int *which_kernel, cudaStream_t s)
 {
+    *which_kernel = 1;
     if constexpr (Q <= 4) {
         if (S >= 2 + OL && S % 2 == 0) { // two bins per step
+            *which_kernel = 2;
             auto kern2 = k_online_ring2<Q, FOLD>;
             if (bytes > 48 * 1024) {
                 cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -464,7 +466,7 @@ cudaError_t launch_t(const LwsbView &v, const OnlineW<Q> &w, const double *thr, 
 
 template <int Q>
 cudaError_t launch_q(const LwsbView &v, const double *const *wr, const double *const *wi, int fold, const double *thr, int iters,
-                     int LA, int R, int pitch, int S, int nt, size_t bytes, unsigned *status, cudaStream_t s)
+                     int LA, int R, int pitch, int S, int nt, size_t bytes, unsigned *status, int *which_kernel, cudaStream_t s)
 {
     OnlineW<Q> w;
     for (int ws = 0; ws < 3; ++ws)
@@ -478,9 +480,9 @@ cudaError_t launch_q(const LwsbView &v, const double *const *wr, const double *c
                 }
                 w.flag[ws][p][r] = f;
             }
-    if (fold == LWSB_FOLD_ANY) return launch_t<Q, LWSB_FOLD_ANY>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, s);
-    if constexpr (Q == 4) { if (fold == LWSB_FOLD_Q4) return launch_t<4, LWSB_FOLD_Q4>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, s); }
-    if constexpr (Q == 2) { if (fold == LWSB_FOLD_Q2) return launch_t<2, LWSB_FOLD_Q2>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, s); }
+    if (fold == LWSB_FOLD_ANY) return launch_t<Q, LWSB_FOLD_ANY>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s);
+    if constexpr (Q == 4) { if (fold == LWSB_FOLD_Q4) return launch_t<4, LWSB_FOLD_Q4>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); }
+    if constexpr (Q == 2) { if (fold == LWSB_FOLD_Q2) return launch_t<2, LWSB_FOLD_Q2>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); }
     return cudaErrorInvalidValue;
 }
 
@@ -489,9 +491,10 @@ cudaError_t launch_q(const LwsbView &v, const double *const *wr, const double *c
 // returns false when this kernel does not serve the shape (the global-memory kernel takes over)
 bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const double *const *wi_host, int fold,
                         const double *thr, int iters, int LA, const int *T_host, size_t smem_limit, unsigned *status,
-                        cudaStream_t s, cudaError_t *err)
+                        cudaStream_t s, cudaError_t *err, int *which_kernel)
 {
     *err = cudaSuccess;
+    *which_kernel = 0;
     const int Q = v.Q;
     if (v.L != OL || !(Q == 2 || Q == 4 || Q == 8)) return false;
     // smallest multiple of Q >= L + 1 (Q > 4: one bin per step) or >= L + 2 (Q <= 4: two bins per step): every thread of a
@@ -510,9 +513,9 @@ bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const d
     nt = (nt + 31) / 32 * 32;
     if (nt > 256) return false;
     switch (Q) {
-    case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, s); break;
-    case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, s); break;
-    case 8: *err = launch_q<8>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, s); break;
+    case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); break;
+    case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); break;
+    case 8: *err = launch_q<8>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); break;
     }
     return true;
 }
