@@ -37,7 +37,7 @@ typedef enum {
     LWSB_ERR_CUDA = -1,        /* CUDA runtime / driver failure (text in lwsb_last_error)      */
     LWSB_ERR_ARG = -2,         /* bad argument (NULL, negative size, unknown enum)              */
     LWSB_ERR_EVEN_NREAL = -3,  /* Nreal even: reference raises ValueError (lws.pyx:223-224)     */
-    LWSB_ERR_UNSUPPORTED = -4, /* Qprime != Q / use_simplifications=False (*fractionalQ paths)  */
+    LWSB_ERR_UNSUPPORTED = -4, /* a shape this build has no kernel for (text in lwsb_last_error) */
     LWSB_ERR_STATE = -5,       /* call order: weights or spectrograms not loaded                */
     LWSB_ERR_NOMEM = -6
 } lwsb_status;
@@ -49,7 +49,9 @@ enum { LWSB_HOST = 0, LWSB_DEVICE = 1 };        /* where the caller's buffers li
 /* flags for the compute calls */
 enum {
     LWSB_FORCE_GENERIC = 1, /* use the generic wavefront kernels even where a tuned one exists  */
-    LWSB_FORCE_ANYQ = 2     /* use the anyQ formulas for Q = 2 / 4 (debug: variant equivalence) */
+    LWSB_FORCE_ANYQ = 2,    /* use the anyQ formulas for Q = 2 / 4 (debug: variant equivalence) */
+    LWSB_FRACTIONAL = 4     /* per-frequency weight rows (the reference's *fractionalQ variants, lws.pyx:246-247, 299-300;
+                               lwslib.cpp:1441): implied whenever the weights were set with Qprime != Q */
 };
 
 /* ---- library / context ------------------------------------------------------------- */

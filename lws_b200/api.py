@@ -125,10 +125,16 @@ def _check_shapes(arrs):
 
 
 def _check_weights(W, use_simplifications):
-    if W.shape[0] != W.shape[1] or not use_simplifications:
-        raise NotImplementedError(
-            'per-frequency weights (frame shift not dividing the frame size, or use_simplifications=False: '
-            'the reference\'s *fractionalQ path) are not supported by the CUDA implementation')
+    """Variant dispatch of lws.pyx:246-247 / 299-300 / lwslib.cpp:1441: per-frequency weight rows (frame shift not dividing
+    the frame size, or use_simplifications=False) select the reference's *fractionalQ variants.  The library recognises
+    them by Qprime != Q; what has no counterpart in the reference is refused here."""
+    W = np.asarray(W)
+    if W.ndim != 3:
+        raise ValueError('weights must have shape (Qprime, Q, L+1)')
+    if not use_simplifications and W.shape[0] == W.shape[1] and W.shape[0] > 1:
+        # summarised weights with use_simplifications=False: the reference would index row n-L of a Q-row table (out of
+        # bounds for every bin beyond Q); create_weights never produces this combination
+        raise ValueError('use_simplifications=False needs per-frequency weights (create_weights(..., use_summarized_weights=False))')
 
 
 def _shard(frames, k):

@@ -127,11 +127,13 @@ struct lwsb_ctx {
     {
         return StatScratch{row_max.as<double>(), leaf_tab.as<const int>(), tab_of.as<const int2>(), leaf_sum.as<double>(), leaf_stride};
     }
+    bool fractional() const { return w[LWSB_W].Qp != w[LWSB_W].Q; } // per-frequency weight rows: the *fractionalQ variants
     LwsbW devw(int which) const
     {
-        const size_t n = (size_t)w[which].Q * w[which].Q * (w[which].L + 1);
+        const bool frac = w[which].Qp != w[which].Q;
+        const size_t n = (size_t)(w[which].Qp + (frac ? 1 : 0)) * w[which].Q * (w[which].L + 1);
         const double *d = raww[which].as<const double>();
-        return LwsbW{d, d + n, reinterpret_cast<const int *>(d + 2 * n)};
+        return LwsbW{d, d + n, reinterpret_cast<const int *>(d + 2 * n), frac ? w[which].Qp : 0};
     }
 };
 
@@ -156,7 +158,7 @@ int use_device(lwsb_ctx *c) { CU(c, cudaSetDevice(c->device)); return LWSB_OK; }
 
 int fold_for(int Q, int flags)
 {
-    if (flags & LWSB_FORCE_ANYQ) return LWSB_FOLD_ANY;
+    if (flags & (LWSB_FORCE_ANYQ | LWSB_FRACTIONAL)) return LWSB_FOLD_ANY; // *fractionalQ = the anyQ formulas, other weight rows
     return Q == 2 ? LWSB_FOLD_Q2 : (Q == 4 ? LWSB_FOLD_Q4 : LWSB_FOLD_ANY); // lws.pyx:246-253
 }
 
@@ -283,22 +285,23 @@ extern "C" int lwsb_set_weights(lwsb_ctx *c, int which, const double *wr, const 
 {
     CHECK_CTX(c);
     if (which < 0 || which > 2 || !wr || !wi || Q < 1 || L < 0) return fail(c, LWSB_ERR_ARG, "bad weight arguments");
-    if (Qprime != Q)
-        return fail(c, LWSB_ERR_UNSUPPORTED,
-                    "per-frequency weights (Qprime != Q: the reference's *fractionalQ path) are not supported");
+    if (Qprime < 1) return fail(c, LWSB_ERR_ARG, "bad weight arguments");
     if (int r = use_device(c)) return r;
     WeightSet &w = c->w[which];
-    w.Q = Q; w.L = L;
-    const size_t n = (size_t)Q * Q * (L + 1);
-    w.wr.assign(wr, wr + n);
-    w.wi.assign(wi, wi + n);
-    // raw copy for the kernels that restate a reference variant literally (NoFuture_LWSQ4)
+    w.Q = Q; w.L = L; w.Qp = Qprime;
+    // Qprime != Q: one weight row per FFT bin (lws.pyx:166-169), the reference's *fractionalQ variants.  They index row
+    // Qprime at the DC bin, one past the table (lwslib.cpp:408); the device table gets that row, zero with the mask clear.
+    const bool frac = Qprime != Q;
+    const size_t n_in = (size_t)Qprime * Q * (L + 1), n = (size_t)(Qprime + (frac ? 1 : 0)) * Q * (L + 1);
+    w.wr.assign(wr, wr + n_in);
+    w.wi.assign(wi, wi + n_in);
+    w.wr.resize(n, 0.0); w.wi.resize(n, 0.0);
     std::vector<int> wf(n);
-    for (size_t i = 0; i < n; ++i) wf[i] = std::hypot(wr[i], wi[i]) > 1.0e-12 ? 1 : 0; // lws.pyx:231-232
+    for (size_t i = 0; i < n; ++i) wf[i] = std::hypot(w.wr[i], w.wi[i]) > 1.0e-12 ? 1 : 0; // lws.pyx:231-232
     CU(c, c->raww[which].reserve(2 * n * sizeof(double) + n * sizeof(int)));
     char *d = c->raww[which].as<char>();
-    CU(c, cudaMemcpyAsync(d, wr, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(d + n * sizeof(double), wi, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d, w.wr.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + n * sizeof(double), w.wi.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(d + 2 * n * sizeof(double), wf.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return LWSB_OK;
@@ -359,6 +362,8 @@ extern "C" int lwsb_load(lwsb_ctx *c, const void *const *S_in, const int *T, int
         // extspec's mirror columns (lws.pyx:153-154) would reach outside the real bins: the reference picks up
         // zeros / already mirrored cells there, an fsize <= 2L corner nobody uses -- refused rather than restated
         return fail(c, LWSB_ERR_UNSUPPORTED, "spectrum narrower than the stencil reach (Nreal <= L) is not supported");
+    if (c->fractional() && c->w[LWSB_W].Qp != 2 * (Nreal - 1))
+        return fail(c, LWSB_ERR_ARG, "per-frequency weights need one row per FFT bin: Qprime == 2 * (Nreal - 1)");
     if (int r = use_device(c)) return r;
     c->B = 0; // invalid until everything below succeeded
     c->stage_valid[0] = c->stage_valid[1] = c->stage_valid[2] = false;
@@ -473,6 +478,11 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
     if (iterations == 0) return LWSB_OK; // lws.pyx:219-220
     if (int r = use_device(c)) return r;
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
+    if (c->fractional()) flags |= LWSB_FRACTIONAL | LWSB_FORCE_GENERIC; // lws.pyx:246-247: Q != Qprime
+    if (flags & LWSB_FRACTIONAL) {
+        if (!c->fractional()) return fail(c, LWSB_ERR_STATE, "the per-frequency update (use_simplifications=False) needs per-frequency weights");
+        flags |= LWSB_FORCE_GENERIC;
+    }
     const int fold = fold_for(c->Q, flags);
     // sweeps whose threshold is not below max|S| cannot move a bin (lwslib.cpp:295-296): the strip kernel drops
     // them, and the plan is sized for the number that remain (largest over the batch)
@@ -563,10 +573,11 @@ extern "C" int lwsb_nofuture(lwsb_ctx *c, int which, const double *thresholds, i
         return fail(c, LWSB_ERR_ARG, "bad lwsb_nofuture arguments");
     if (int r = check_resident(c)) return r;
     if (iterations == 0) return LWSB_OK; // lws.pyx:272-273
-    if (!c->w[which].valid() || c->w[which].Q != c->Q || c->w[which].L != c->L)
+    if (!c->w[which].valid() || c->w[which].Q != c->Q || c->w[which].L != c->L || c->w[which].Qp != c->w[LWSB_W].Qp)
         return fail(c, LWSB_ERR_STATE, "no-future weight set missing or of a different shape than LWSB_W");
     if (int r = use_device(c)) return r;
     if (int r = upload_thresholds(c, thresholds, iterations)) return r;
+    if (c->fractional()) flags |= LWSB_FRACTIONAL; // lws.pyx:299-300
     const int fold = fold_for(c->Q, flags);
     if (int r = begin_compute(c, 0)) return r;
     if (fold == LWSB_FOLD_Q4) // NoFuture_LWSQ4, reproduced as written (lwslib.cpp:538-617)
@@ -585,8 +596,9 @@ extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations
     if (int r = check_resident(c)) return r;
     if (iterations == 0) return LWSB_OK; // lws.pyx:332-333
     for (int i = 1; i < 3; ++i)
-        if (!c->w[i].valid() || c->w[i].Q != c->Q || c->w[i].L != c->L)
+        if (!c->w[i].valid() || c->w[i].Q != c->Q || c->w[i].L != c->L || c->w[i].Qp != c->w[LWSB_W].Qp)
             return fail(c, LWSB_ERR_STATE, "online mode needs W, W_ai and W_af of the same shape");
+    if (c->fractional()) flags |= LWSB_FRACTIONAL | LWSB_FORCE_GENERIC; // lwslib.cpp:1441: !use_summarized_weights
     if (c->Nreal > online_generic_max_nreal(c->L))
         return fail(c, LWSB_ERR_UNSUPPORTED, "spectrum too wide for the online kernel");
     if (int r = use_device(c)) return r;

@@ -22,9 +22,11 @@
 
 namespace lwsb {
 
-struct LwsbW {        // one weight set in the reference's layout (Qprime = Q, Q, L+1)
+struct LwsbW {        // one weight set in the reference's layout (Qprime, Q, L+1)
     const double *wr, *wi;
     const int *wf;    // |W| > 1e-12 (lws.pyx:231-232)
+    int frac_rows;    // 0: summarised weights (Qprime = Q, row = bin mod Q); N = 2(Nreal-1): one row per FFT bin (the
+                      // reference's *fractionalQ variants), the device table has N + 1 rows, row N zero / mask clear
 };
 
 // acc += w*b + conj(w)*c  (lwslib.cpp:98-99)
@@ -122,13 +124,17 @@ __device__ __forceinline__ void x_left(const Acc &E, const LwsbW &w, int L, int 
 // sweep = (1, 0), online row updates as Asym_UpdatePhase* derives them (lwslib.cpp:1141-1151).
 // The `update == 1` branch of Asym_UpdatePhase* (centre-bin term) is not restated: both
 // reference bindings pass update = 2 (lws.pyx:363, online_lws.cpp:160).
+// `bin` is the bin index n - L: the weight rows are bin mod Q and (Q - bin mod Q) mod Q, or -- per-frequency tables,
+// lwslib.cpp:393, 408 -- bin and N - bin (row N, which the reference reads one past its table at the DC bin, is the
+// zero row the host appends: those terms are skipped).
 template <class Acc>
-__device__ __forceinline__ void x_weighted_sum(const Acc &E, const LwsbW &w, int Q, int L, int p, int fold, int rframe,
+__device__ __forceinline__ void x_weighted_sum(const Acc &E, const LwsbW &w, int Q, int L, int bin, int fold, int rframe,
                                                int cframe, double &tr, double &ti)
 {
     tr = 0.0; ti = 0.0;
-    const int wp = p * Q * (L + 1);
-    const int wpn = ((Q - p) % Q) * Q * (L + 1);
+    const int p = bin % Q;
+    const int wp = (w.frac_rows ? bin : p) * Q * (L + 1);
+    const int wpn = (w.frac_rows ? w.frac_rows - bin : (Q - p) % Q) * Q * (L + 1);
     if (cframe)
         for (int k = 1; k <= L; ++k)
             if (w.wf[wp + k]) {

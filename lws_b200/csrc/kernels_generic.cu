@@ -222,7 +222,7 @@ __device__ __forceinline__ void update_bin(const LwsbView &v, const LwsbW &w, in
     if (!(a > thr)) return; // lwslib.cpp:295-296
     const GlobalCell cell{Erow + v.c0 + c, v.P};
     double tr, ti;
-    x_weighted_sum(cell, w, v.Q, v.L, c % v.Q, fold, rframe, cframe, tr, ti);
+    x_weighted_sum(cell, w, v.Q, v.L, c, fold, rframe, cframe, tr, ti);
     double2 val;
     if (x_project(tr, ti, a, val)) {
         // lwslib.cpp:356-368: store, then refresh the mirrored copies at once

@@ -19,6 +19,7 @@ namespace lwsb {
 
 struct WeightSet {
     int Q = 0, L = 0;
+    int Qp = 0; // rows: Q (summarised weights) or one per FFT bin (the reference's *fractionalQ variants)
     std::vector<double> wr, wi; // (Q, Q, L+1)
     bool valid() const { return Q > 0; }
     size_t idx(int p, int r, int k) const { return ((size_t)p * Q + r) * (L + 1) + k; }

@@ -26,7 +26,16 @@
 #include <math.h>
 #include <stddef.h>
 
-enum { FOLD_ANY = 0, FOLD_Q2 = 2, FOLD_Q4 = 4 };
+/* FOLD_FRAC: the reference's *fractionalQ variants (lwslib.cpp:376-467, 693-764, 1276-1421): the anyQ formulas with one
+ * weight row PER FREQUENCY BIN -- row (n-L) for the "mod" terms, row N-(n-L), N = 2(Nreal-1), for the "modneg" terms
+ * (lwslib.cpp:393, 408).  At the DC bin the reference reads row N of a table that has rows 0..N-1 (create_weights builds
+ * T = N rows, lws.pyx:166-178): an out-of-bounds read whose outcome depends on the heap (measured: the compiled reference
+ * returns different results for repeated calls on the same input).  The oracle -- and the CUDA path -- define it: the
+ * caller hands a table with N+1 rows whose row N is zero (mask clear), i.e. the modneg terms of the DC bin are skipped,
+ * which is what the reference does whenever the memory behind its mask array happens to be zero (the common case for the
+ * small tables of the tests).  tests/test_oracle_vs_ref.py pins this against the reference's own C functions called
+ * on such padded tables. */
+enum { FOLD_ANY = 0, FOLD_FRAC = 1, FOLD_Q2 = 2, FOLD_Q4 = 4 };
 
 typedef struct {
     double *Sr, *Si;          /* extended spectrogram, (M+2(Q-1)) x Np, updated in place   */
@@ -138,9 +147,15 @@ static void update_row(const lws_t *c, int m, int fold, int rframe, int cframe, 
         const double a = c->amp[m * Np + n];
         if (!(a > thr)) continue;
         cacc t = {0., 0.};
-        const int p = (n - L) % Q;
-        const int wp = p * Q * (L + 1);
-        const int wpn = ((Q - p) % Q) * Q * (L + 1);
+        int wp, wpn;
+        if (fold == FOLD_FRAC) { /* lwslib.cpp:393, 408: rows n-L and N-(n-L) of the per-frequency table */
+            wp = (n - L) * Q * (L + 1);
+            wpn = (2 * (c->Nreal - 1) - (n - L)) * Q * (L + 1);
+        } else {
+            const int p = (n - L) % Q;
+            wp = p * Q * (L + 1);
+            wpn = ((Q - p) % Q) * Q * (L + 1);
+        }
         if (cframe) {
             if (update == 1) { /* never taken through the Python binding (lws.pyx:363 passes 2) */
                 t.r += c->Sr[m * Np + n] / qdiv;
@@ -161,8 +176,9 @@ static void update_row(const lws_t *c, int m, int fold, int rframe, int cframe, 
             if (2 < rframe) both_sides(c, &t, m, n, 2, wp, wpn, fold, 0);
             else            left_side(c, &t, m, n, 2, wp, wpn, fold, 0);
         } else {
-            for (int r = 1; r < rframe; r++) both_sides(c, &t, m, n, r, wp, wpn, fold, 0);
-            for (int r = rframe; r < Q; r++) left_side(c, &t, m, n, r, wp, wpn, fold, 0);
+            const int f = fold == FOLD_FRAC ? FOLD_ANY : fold; /* same formulas as anyQ, other weight rows */
+            for (int r = 1; r < rframe; r++) both_sides(c, &t, m, n, r, wp, wpn, f, 0);
+            for (int r = rframe; r < Q; r++) left_side(c, &t, m, n, r, wp, wpn, f, 0);
         }
         commit_bin(c, m, n, t, a);
     }
@@ -242,7 +258,7 @@ void orc_amp_spec(const double *Sr, const double *Si, double *amp, int size)
     for (int n = 0; n < size; n++) amp[n] = sqrt(Sr[n] * Sr[n] + Si[n] * Si[n]);
 }
 
-/* One batch sweep.  fold = 2 / 4 / 0 selects LWSQ2 / LWSQ4 / LWSanyQ. */
+/* One batch sweep.  fold = 2 / 4 / 0 / 1 selects LWSQ2 / LWSQ4 / LWSanyQ / LWSfractionalQ. */
 void orc_batch_sweep(int fold, double *Sr, double *Si, const double *wr, const double *wi, const int *wf,
                      const double *amp, int Nreal, int M, int L, int Q, double thr)
 {
@@ -275,7 +291,7 @@ void orc_asym_update(int fold, double *Sr, double *Si, const double *wr, const d
     }
 }
 
-/* TF_RTISI_LA (lwslib.cpp:1424-1492), summarised-weights branches only. */
+/* TF_RTISI_LA (lwslib.cpp:1424-1492); fold = FOLD_FRAC is its !use_summarized_weights branch. */
 void orc_rtisi_la(int fold, double *Sr, double *Si, const double *wr, const double *wi, const double *wr_ai,
                   const double *wi_ai, const double *wr_af, const double *wi_af, const int *wf, const int *wf_ai,
                   const int *wf_af, const double *amp, int iter, int LA, int Nreal, int M, int L, int Q,

@@ -22,6 +22,10 @@ void ref_NoFuture_LWSQ2(SWEEP_ARGS, int Nreal, int M, int L, double thr) { NoFut
 void ref_NoFuture_LWSQ4(SWEEP_ARGS, int Nreal, int M, int L, double thr) { NoFuture_LWSQ4(Sr, Si, wr, wi, wf, amp, Nreal, M, L, thr); }
 void ref_NoFuture_LWSanyQ(SWEEP_ARGS, int Nreal, int M, int L, int Q, double thr) { NoFuture_LWSanyQ(Sr, Si, wr, wi, wf, amp, Nreal, M, L, Q, thr); }
 
+void ref_NoFuture_LWSfractionalQ(SWEEP_ARGS, int Nreal, int M, int L, int Q, double thr) { NoFuture_LWSfractionalQ(Sr, Si, wr, wi, wf, amp, Nreal, M, L, Q, thr); }
+void ref_Asym_UpdatePhasefractionalQ(SWEEP_ARGS, int Nreal, int M, int M0, int L, int Q, double Qfloat, double thr, int update)
+{ Asym_UpdatePhasefractionalQ(Sr, Si, wr, wi, wf, amp, Nreal, M, M0, L, Q, Qfloat, thr, update); }
+
 void ref_Asym_UpdatePhaseQ2(SWEEP_ARGS, int Nreal, int M, int M0, int L, double thr, int update)
 { Asym_UpdatePhaseQ2(Sr, Si, wr, wi, wf, amp, Nreal, M, M0, L, thr, update); }
 void ref_Asym_UpdatePhaseQ4(SWEEP_ARGS, int Nreal, int M, int M0, int L, double thr, int update)

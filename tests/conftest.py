@@ -24,12 +24,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-def load_cases():
+def load_cases(key="cases"):
     with open(os.path.join(GOLDEN, "cases.json")) as f:
-        return json.load(f)["cases"]
+        return json.load(f)[key]
 
 
 CASES = load_cases()
+FRAC_CASES = load_cases("fractional_cases")  # the *fractionalQ paths: hop not dividing the frame size / use_simplifications=False
 SMALL_CASES = [c for c in CASES if c["name"] not in ("cfg1_short",)]
 
 
@@ -80,3 +81,40 @@ def make_signal(kind, seed, n):
     x = sum(np.sin(k * ph) / k for k in range(1, 30))
     x = x * (0.5 + 0.5 * np.sin(2 * np.pi * 2 * t)) ** 2
     return x + 0.01 * np.random.default_rng(seed).standard_normal(n)
+
+
+# ---------------------------------------------------------------------------------- *fractionalQ reference driver
+def ref_fractional(ref_module, stage, S, W, thresholds, W_ai=None, W_af=None, LA=3):
+    """The reference's *fractionalQ C functions (lwslib.cpp:376-467, 693-764, 1276-1492) driven the way its binding
+    drives them (lws.pyx:209-375), but on weight tables with a zero row N appended: the reference reads that row, one
+    past its table, at the DC bin -- undefined behaviour that makes the compiled module's results depend on the heap.
+    With the padded tables the reference's own code is deterministic; oracle and CUDA path are pinned to it."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "liblws_ref.so"))
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    d = lambda a: a.ctypes.data_as(dp)
+    S = np.asarray(S).astype(np.complex128)
+    L, Q = W.shape[2] - 1, W.shape[1]
+    T, Nreal = S.shape
+
+    def split(Wx):
+        Wp = np.concatenate([Wx, np.zeros_like(Wx[:1])], axis=0)
+        return (np.ascontiguousarray(Wp.real), np.ascontiguousarray(Wp.imag),
+                np.ascontiguousarray(np.abs(Wp) > 1.0e-12, dtype=np.intc))
+    E = ref_module.extspec(S, L, Q)
+    Er, Ei = np.ascontiguousarray(E.real), np.ascontiguousarray(E.imag)
+    amp = np.ascontiguousarray(np.abs(E))
+    mean = np.mean(np.abs(S))
+    wr, wi, wf = split(W)
+    if stage in ("batch", "nofuture"):
+        fn = lib.ref_LWSfractionalQ if stage == "batch" else lib.ref_NoFuture_LWSfractionalQ
+        for t in thresholds:
+            fn(d(Er), d(Ei), d(wr), d(wi), wf.ctypes.data_as(ip), d(amp), Nreal, T, L, Q, ctypes.c_double(t * mean))
+    else:
+        ar, ai, af = split(W_ai)
+        fr, fi, ff = split(W_af)
+        thr = np.ascontiguousarray(np.asarray(thresholds, dtype=np.float64) * mean)
+        lib.ref_TF_RTISI_LA(d(Er), d(Ei), d(wr), d(wi), d(ar), d(ai), d(fr), d(fi), wf.ctypes.data_as(ip), af.ctypes.data_as(ip),
+                            ff.ctypes.data_as(ip), d(amp), len(thr), int(LA), Nreal, T, L, Q, ctypes.c_double(float(Q)),  # Qfloat: read only when update == 1
+                            0, d(thr), 2)
+    return Er[(Q - 1):(Q - 1 + T), L:(Nreal + L)] + 1j * Ei[(Q - 1):(Q - 1 + T), L:(Nreal + L)]

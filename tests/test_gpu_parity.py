@@ -110,6 +110,50 @@ def test_golden_transforms(gpu, case, capsys):
         assert abs(p.get_consistency(g["Sc"]) - float(g["consistency"])) < 1e-6
 
 
+from conftest import FRAC_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", FRAC_CASES, ids=[c["name"] for c in FRAC_CASES])
+def test_fractional_paths_match_golden(gpu, case):
+    """hop not dividing the frame size / use_simplifications=False (LWSfractionalQ, NoFuture_LWSfractionalQ,
+    Asym_UpdatePhasefractionalQ: per-frequency weight rows): golden vectors from the reference's C functions on tables with
+    the zero row N that the reference reads out of bounds at the DC bin (tests/conftest.py::ref_fractional)."""
+    g = golden(case["name"])
+    p = gpu.lws(*case["args"], mode="music", **case["kwargs"])
+    for k in ("W", "W_ai", "W_af"):
+        assert np.array_equal(getattr(p, k), g[k]), k
+    A = np.abs(g["X"])
+    checks = {
+        "batch_zero": lambda: p.batch_lws(A, thresholds=np.zeros(5)),
+        "batch_mid": lambda: p.batch_lws(A, thresholds=g["thr_mid"]),
+        "batch_cplx": lambda: p.batch_lws(g["Sc"], thresholds=np.zeros(3)),
+        "nofuture_def": lambda: p.nofuture_lws(A),
+        "nofuture_zero": lambda: p.nofuture_lws(A, thresholds=np.zeros(2)),
+        "online_def": lambda: p.online_lws(A, iterations=3),
+        "online_zero": lambda: p.online_lws(g["Sc"], thresholds=np.zeros(2)),
+    }
+    for k, fn in checks.items():
+        _close(fn(), g[k], case["name"] + ":" + k)
+    pr = gpu.lws(*case["args"], mode="music", batch_iterations=8, batch_alpha=1.0, **case["kwargs"])
+    _close(pr.run_lws(A), g["run"], case["name"] + ":run")
+    X = p.stft(g["x"])
+    assert np.abs(X - g["X"]).max() <= 1e-12 * max(1.0, np.abs(g["X"]).max())
+
+
+@pytest.mark.parametrize("fs,hop,kw,n", [(512, 100, {}, 16000), (256, 64, {"use_simplifications": False}, 9000), (200, 48, {"look_ahead": 1}, 7000)])
+def test_fractional_paths_vs_oracle(gpu, oracle, fs, hop, kw, n):
+    """The reference's README case lws.lws(512, 100) (Q = 5.12, W of shape (512, 6, 6)) and friends against the oracle,
+    single and ragged batch."""
+    po, pg = oracle.lws(fs, hop, mode="music", batch_iterations=20, batch_alpha=2, **kw), gpu.lws(fs, hop, mode="music", batch_iterations=20, batch_alpha=2, **kw)
+    assert pg.W.shape[0] == fs and np.array_equal(pg.W, po.W)
+    As = [np.abs(po.stft(make_signal(k, 41 + i, n - 900 * i))) for i, k in enumerate(("tonal", "white"))]
+    for A, Y in zip(As, pg.batch_lws(As)):
+        _close(Y, po.batch_lws(A), "fractional batch")
+    for A, Y in zip(As, pg.run_lws(As)):
+        _close(Y, po.run_lws(A), "fractional run_lws")
+    _close(pg.online_lws(As[1]), po.online_lws(As[1]), "fractional online")
+
+
 def test_forced_anyq_equals_folded(gpu):
     """Q2 / Q4 shortcuts vs the anyQ formulas: equal to ~1e-10."""
     from lws_b200 import _native
@@ -188,8 +232,7 @@ def test_api_behaviours(gpu):
     xx = np.random.default_rng(4).standard_normal(1000)
     assert np.abs(p.istft(p.stft(xx))[:1000] - xx).max() < 1e-13
     assert p.get_consistency(p.stft(xx)) > 250.0
-    with pytest.raises(NotImplementedError):
-        gpu.lws(512, 100).batch_lws(np.ones((4, 257)), iterations=1)
+    assert gpu.lws(512, 100).W.shape == (512, 6, 6)  # per-frequency weights: the *fractionalQ path (test_fractional_*)
 
 
 def test_full_size_properties(gpu):

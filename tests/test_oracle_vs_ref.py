@@ -174,3 +174,51 @@ def test_python_api_vs_live_reference(oracle, ref_module, case, capsys):
     assert np.array_equal(a.batch_lws(A, thresholds=thr), b.batch_lws(A, thresholds=thr))
     assert np.array_equal(a.online_lws(A, thresholds=thr), b.online_lws(A, thresholds=thr))
     assert np.array_equal(a.nofuture_lws(A, thresholds=thr), b.nofuture_lws(A, thresholds=thr))
+
+
+# ---------------------------------------------------------------------------------- *fractionalQ paths
+from conftest import FRAC_CASES, ref_fractional, make_signal  # noqa: E402
+
+FRAC_NAMES = [c["name"] for c in FRAC_CASES]
+
+
+def _frac_checks(p, g):
+    A = np.abs(g["X"])
+    return {
+        "batch_zero": lambda: p.batch_lws(A, thresholds=np.zeros(5)),
+        "batch_mid": lambda: p.batch_lws(A, thresholds=g["thr_mid"]),
+        "batch_cplx": lambda: p.batch_lws(g["Sc"], thresholds=np.zeros(3)),
+        "nofuture_def": lambda: p.nofuture_lws(A),
+        "nofuture_zero": lambda: p.nofuture_lws(A, thresholds=np.zeros(2)),
+        "online_def": lambda: p.online_lws(A, iterations=3),
+        "online_zero": lambda: p.online_lws(g["Sc"], thresholds=np.zeros(2)),
+    }
+
+
+@pytest.mark.parametrize("case", FRAC_CASES, ids=FRAC_NAMES)
+def test_fractional_paths_match_golden(oracle, case):
+    """hop not dividing the frame size / use_simplifications=False: per-frequency weight rows (LWSfractionalQ & co.);
+    golden vectors from the reference's C functions on tables with the zero row N the reference reads out of bounds"""
+    g = golden(case["name"])
+    p = oracle.lws(*case["args"], mode="music", **case["kwargs"])
+    for k in ("awin", "swin", "W", "W_ai", "W_af"):
+        assert np.array_equal(getattr(p, k), g[k]), k
+    assert p.W.shape[0] == 2 * (g["X"].shape[1] - 1) and p.W.shape[0] != p.W.shape[1]
+    for k, fn in _frac_checks(p, g).items():
+        assert np.array_equal(fn(), g[k]), k
+    pr = oracle.lws(*case["args"], mode="music", batch_iterations=8, batch_alpha=1.0, **case["kwargs"])
+    assert np.array_equal(pr.run_lws(np.abs(g["X"])), g["run"])
+
+
+@pytest.mark.parametrize("fs,hop,kw", [(64, 20, {}), (32, 8, {"use_simplifications": False}), (128, 48, {"look_ahead": 1}), (60, 12, {"use_simplifications": False})])
+def test_fractional_oracle_vs_reference_functions(oracle, ref_module, fs, hop, kw):
+    """fresh inputs: oracle == the reference's *fractionalQ functions (zero row N appended to the tables), bit for bit"""
+    po, pr = oracle.lws(fs, hop, mode="music", **kw), ref_module.lws(fs, hop, mode="music", **kw)
+    for k in ("W", "W_ai", "W_af"):
+        assert np.array_equal(getattr(po, k), getattr(pr, k))
+    A = np.abs(pr.stft(make_signal("tonal", 9, 2500)))
+    thr = oracle.get_thresholds(4, 1.5, 0.3, 1)
+    assert np.array_equal(po.batch_lws(A, thresholds=thr), ref_fractional(ref_module, "batch", A, pr.W, thr))
+    assert np.array_equal(po.nofuture_lws(A, thresholds=thr[:2]), ref_fractional(ref_module, "nofuture", A, pr.W_ai, thr[:2]))
+    assert np.array_equal(po.online_lws(A, thresholds=thr[:3]),
+                          ref_fractional(ref_module, "online", A, pr.W, thr[:3], pr.W_ai, pr.W_af, pr.look_ahead))

@@ -111,9 +111,41 @@ def main():
     cases.append(dict(name="cfg1_short", args=[512, 128], kwargs={}, signal="tonal", n=6000, seed=5,
                       T=int(A.shape[0]), Nreal=int(A.shape[1])))
 
+    # the *fractionalQ paths (frame shift not dividing the frame size / use_simplifications=False): per-frequency weight
+    # rows.  The compiled module reads one row past its table at the DC bin (undefined: its output varies from call to
+    # call), so these vectors come from the reference's C functions driven on tables with a zero row appended
+    # (tests/conftest.py::ref_fractional); windows, weights and transforms are the module's.
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import ref_fractional
+    frac = []
+    for name, args, kw, kind, n in [("frac_64_20", (64, 20), {}, "white", 1500), ("frac_nosimp_32_8", (32, 8), {"use_simplifications": False}, "tonal", 600),
+                                    ("frac_48_10", (48, 10), {"look_ahead": 2}, "white", 900)]:
+        seed = 200 + len(frac)
+        x = white(seed, n) if kind == "white" else tonal(seed, n)
+        ref = lws_ref.lws(*args, mode="music", **kw)
+        X = ref.stft(x)
+        A = np.abs(X)
+        rng = np.random.default_rng(100 + seed)
+        Sc = A * np.exp(1j * rng.uniform(0, 2 * np.pi, A.shape))
+        thr_mid = lws_ref.get_thresholds(6, 2.0, 0.4, 1)
+        on_thr = lws_ref.get_thresholds(3, 1, 0.1, 1)
+        nf = ref_fractional(lws_ref, "nofuture", A, ref.W_ai, lws_ref.get_thresholds(1, 1, 0.1, 1))
+        on = ref_fractional(lws_ref, "online", nf, ref.W, lws_ref.get_thresholds(10, 1, 0.1, 1), ref.W_ai, ref.W_af, ref.look_ahead)
+        d = dict(x=x, awin=ref.awin, swin=ref.swin, W=ref.W, W_ai=ref.W_ai, W_af=ref.W_af, X=X, xrec=ref.istft(X), Sc=Sc, thr_mid=thr_mid,
+                 batch_zero=ref_fractional(lws_ref, "batch", A, ref.W, np.zeros(5)),
+                 batch_mid=ref_fractional(lws_ref, "batch", A, ref.W, thr_mid),
+                 batch_cplx=ref_fractional(lws_ref, "batch", Sc, ref.W, np.zeros(3)),
+                 nofuture_def=nf,
+                 nofuture_zero=ref_fractional(lws_ref, "nofuture", A, ref.W_ai, np.zeros(2)),
+                 online_def=ref_fractional(lws_ref, "online", A, ref.W, on_thr, ref.W_ai, ref.W_af, ref.look_ahead),
+                 online_zero=ref_fractional(lws_ref, "online", Sc, ref.W, np.zeros(2), ref.W_ai, ref.W_af, ref.look_ahead),
+                 run=ref_fractional(lws_ref, "batch", on, ref.W, lws_ref.get_thresholds(8, 1.0, 0.1, 1)))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        frac.append(dict(name=name, args=list(args), kwargs=kw, signal=kind, n=n, seed=seed, T=int(A.shape[0]), Nreal=int(A.shape[1])))
+
     with open(os.path.join(OUT, "cases.json"), "w") as f:
         json.dump(dict(generator="tools/make_golden.py", reference="Jonathan-LeRoux/lws v%s" % lws_ref.__version__,
-                       numpy=np.__version__, cases=cases), f, indent=1)
+                       numpy=np.__version__, cases=cases, fractional_cases=frac), f, indent=1)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("wrote %d cases, %.2f MB" % (len(cases), tot / 1e6))
 
