@@ -64,6 +64,11 @@ const char *lwsb_last_error(const lwsb_ctx *ctx); /* ctx may be NULL: error of t
 int lwsb_create(int device, void *stream, lwsb_ctx **out);
 int lwsb_destroy(lwsb_ctx *ctx);
 int lwsb_sync(lwsb_ctx *ctx);                /* wait for everything queued on the stream       */
+/* Page-locked host memory (cudaHostAlloc, portable across devices): buffers the DMA engines reach directly.  Pageable
+ * host buffers are accepted everywhere too -- the library stages them through pinned chunks with a few host threads
+ * (env LWSB_HOST_THREADS) -- but a pinned result buffer saves that pass and the page faults of fresh memory. */
+int lwsb_host_alloc(unsigned long long bytes, void **out);
+int lwsb_host_free(void *p);
 
 /* ---- weights: replaces the Wr/Wi/Wflag marshalling of lws.pyx:227-232, 341-352 -------- */
 int lwsb_set_weights(lwsb_ctx *ctx, int which, const double *wr, const double *wi, int Qprime, int Q, int L);

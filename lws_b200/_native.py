@@ -31,6 +31,8 @@ SIGNATURES = {
     "lwsb_create": (_ci, [_ci, _vp, _vpp]),
     "lwsb_destroy": (_ci, [_vp]),
     "lwsb_sync": (_ci, [_vp]),
+    "lwsb_host_alloc": (_ci, [ctypes.c_ulonglong, _vpp]),
+    "lwsb_host_free": (_ci, [_vp]),
     "lwsb_set_weights": (_ci, [_vp, _ci, _dp, _dp, _ci, _ci, _ci]),
     "lwsb_create_weights": (_ci, [_dp, _dp, _ci, _ci, _ci, _ci, _dp, _dp, _ip, _ip]),
     "lwsb_load": (_ci, [_vp, _vpp, _ip, _ci, _ci, _ci, _ci]),

@@ -16,7 +16,7 @@ import threading
 
 import numpy as np
 
-from . import _native, dsp
+from . import _native, _pinned, dsp
 from .dsp import get_thresholds
 
 _EVEN = 'Please only include non-negative frequencies in the input spectrogram.'
@@ -75,19 +75,19 @@ def _as_batch(S):
     return arrs, (_native.C128 if cplx else _native.F64), shape
 
 
-def _rebuild(outs, shape, out=None):
+def _rebuild(outs, shape, out=None, whole=None):
     if out is not None:
         return out
     if shape == "2d":
         return outs[0]
     if shape == "3d":
-        return np.stack(outs) if not _is_views_of_one(outs) else outs[0].base
+        return whole if whole is not None else np.stack(outs)
     return outs
 
 
-def _is_views_of_one(outs):
-    b = outs[0].base
-    return b is not None and b.ndim == 3 and all(o.base is b for o in outs)
+class _Outs(list):
+    """per-utterance result arrays; `whole` is the (B, T, Nreal) array they are slices of, if any"""
+    whole = None
 
 
 def _alloc_outs(arrs, shape, out=None):
@@ -100,10 +100,13 @@ def _alloc_outs(arrs, shape, out=None):
         if len(outs) != len(arrs):
             raise ValueError('out= does not match the batch')
         return outs
+    # fresh result arrays, as the reference returns them -- in page-locked memory where that pays (_pinned.py)
     if shape == "3d":
-        big = np.empty((len(arrs),) + arrs[0].shape, dtype=np.complex128)
-        return [big[b] for b in range(len(arrs))]
-    return [np.empty(a.shape, dtype=np.complex128) for a in arrs]
+        big = _pinned.empty((len(arrs),) + arrs[0].shape)
+        outs = _Outs(big[b] for b in range(len(arrs)))
+        outs.whole = big
+        return outs
+    return _Outs(_pinned.empty(a.shape) for a in arrs)
 
 
 def _passthrough(S):
@@ -199,7 +202,7 @@ def batch_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=
         ctx.batch_lws(a, kind, thresholds, flags, outs=o)
 
     _run_sharded(_devices(device), arrs, outs, fn, overlap=True)
-    return _rebuild(outs, shape, out)
+    return _rebuild(outs, shape, out, getattr(outs, 'whole', None))
 
 
 def nofuture_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=0, out=None):
@@ -216,7 +219,7 @@ def nofuture_lws(S, W, thresholds, use_simplifications=True, *, device=None, fla
         ctx.nofuture_lws(_native.W, a, kind, thresholds, flags, outs=o)
 
     _run_sharded(_devices(device), arrs, outs, fn)
-    return _rebuild(outs, shape, out)
+    return _rebuild(outs, shape, out, getattr(outs, 'whole', None))
 
 
 def online_lws(S, W, W_ai, W_af, thresholds, LA, fshift, use_simplifications=True, *, device=None, flags=0, out=None):
@@ -235,7 +238,7 @@ def online_lws(S, W, W_ai, W_af, thresholds, LA, fshift, use_simplifications=Tru
         ctx.online_lws(a, kind, thresholds, int(LA), flags, outs=o)
 
     _run_sharded(_devices(device), arrs, outs, fn)
-    return _rebuild(outs, shape, out)
+    return _rebuild(outs, shape, out, getattr(outs, 'whole', None))
 
 
 class lws(object):
@@ -409,4 +412,4 @@ class lws(object):
             ctx.run_lws(a, kind, nf, on, self.look_ahead, ba, outs=o)
 
         _run_sharded(_devices(self.device), arrs, outs, fn)
-        return _rebuild(outs, shape, out)
+        return _rebuild(outs, shape, out, getattr(outs, 'whole', None))

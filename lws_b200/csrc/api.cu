@@ -12,6 +12,7 @@
 #include <string>
 #include <tuple>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/lws_b200.h"
@@ -63,6 +64,41 @@ std::mutex &strip_mutex(int device)
     return m[(unsigned)device % 64u];
 }
 
+// ---------------------------------------------------------------- host staging
+// A caller of the reference hands pageable numpy arrays.  cudaMemcpyAsync from pageable memory goes through the
+// driver's own staging at 5-6 GB/s (measured: 85 ms for the 495 MB of BASELINE configs[1], against 10 ms from pinned
+// memory).  Pageable sources / destinations are therefore staged through two pinned buffers of the context: a few host
+// threads copy chunk k + 1 while the DMA engine moves chunk k.
+int host_threads()
+{
+    static int n = [] {
+        if (const char *e = getenv("LWSB_HOST_THREADS")) return std::max(1, atoi(e));
+        const unsigned hw = std::thread::hardware_concurrency();
+        return (int)std::min(8u, std::max(1u, hw / 4));
+    }();
+    return n;
+}
+
+void parallel_memcpy(char *dst, const char *src, size_t bytes)
+{
+    const int nt = bytes < (4u << 20) ? 1 : host_threads();
+    if (nt == 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = (bytes / nt + 4095) & ~(size_t)4095;
+    for (int i = 0; i < nt; ++i) {
+        const size_t lo = std::min(bytes, per * i), hi = std::min(bytes, per * (i + 1));
+        if (hi > lo) th.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+    }
+    for (auto &t : th) t.join();
+}
+
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 } // namespace
 
 struct lwsb_ctx {
@@ -103,6 +139,9 @@ struct lwsb_ctx {
     std::map<int, DevBuf> twiddles;        // exp(-2 pi i j / N) tables by N
     std::vector<void *> hptr;
 
+    void *pin[2] = {nullptr, nullptr};     // pinned staging for pageable host buffers (lwsb_load / lwsb_store)
+    size_t pin_cap = 0;
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_valid = false;
     // per-stage device times since the last lwsb_load: 0 nofuture, 1 online, 2 batch (lwsb_last_stage_ms)
@@ -194,6 +233,88 @@ int check_resident(lwsb_ctx *c)
     return LWSB_OK;
 }
 
+constexpr size_t PIN_CHUNK = 24u << 20; // bytes per staging buffer
+
+int ensure_pinned(lwsb_ctx *c)
+{
+    if (c->pin[0]) return LWSB_OK;
+    for (int i = 0; i < 2; ++i) {
+        CU(c, cudaHostAlloc(&c->pin[i], PIN_CHUNK, cudaHostAllocDefault));
+        CU(c, cudaEventCreateWithFlags(&c->pin_ev[i], cudaEventDisableTiming));
+    }
+    c->pin_cap = PIN_CHUNK;
+    return LWSB_OK;
+}
+
+// B host arrays (sizes[b] bytes each) <-> consecutive device ranges dev + offs[b].  Pinned host arrays are copied
+// directly; pageable ones go through the two pinned buffers in chunks, host threads copying one chunk while the DMA
+// engine moves the other.  to_device = false: the device data must already be complete on the stream.
+int staged_copy(lwsb_ctx *c, char *dev, const std::vector<size_t> &offs, const std::vector<size_t> &sizes, void *const *host, bool to_device)
+{
+    const int B = (int)sizes.size();
+    bool any_pageable = false;
+    for (int b = 0; b < B && !any_pageable; ++b) any_pageable = is_pageable(host[b]);
+    if (!any_pageable) {
+        for (int b = 0; b < B; ++b)
+            CU(c, to_device ? cudaMemcpyAsync(dev + offs[b], host[b], sizes[b], cudaMemcpyHostToDevice, c->stream)
+                            : cudaMemcpyAsync(host[b], dev + offs[b], sizes[b], cudaMemcpyDeviceToHost, c->stream));
+        return LWSB_OK;
+    }
+    if (int r = ensure_pinned(c)) return r;
+    // pieces of at most PIN_CHUNK bytes: (array, offset inside it, bytes)
+    struct Piece { int b; size_t off, n; };
+    std::vector<std::vector<Piece>> chunks(1);
+    size_t fill = 0;
+    for (int b = 0; b < B; ++b)
+        for (size_t o = 0; o < sizes[b];) {
+            if (fill == PIN_CHUNK) { chunks.emplace_back(); fill = 0; }
+            const size_t n = std::min(sizes[b] - o, PIN_CHUNK - fill);
+            chunks.back().push_back(Piece{b, o, n});
+            o += n; fill += n;
+        }
+    const int nc = (int)chunks.size();
+    auto host_side = [&](int k) { // copy chunk k between the caller's arrays and pinned buffer k % 2
+        char *pb = (char *)c->pin[k % 2];
+        size_t at = 0;
+        for (const Piece &pc : chunks[k]) {
+            if (to_device) parallel_memcpy(pb + at, (const char *)host[pc.b] + pc.off, pc.n);
+            else parallel_memcpy((char *)host[pc.b] + pc.off, pb + at, pc.n);
+            at += pc.n;
+        }
+    };
+    auto dma = [&](int k) -> cudaError_t {
+        char *pb = (char *)c->pin[k % 2];
+        size_t at = 0;
+        for (const Piece &pc : chunks[k]) {
+            cudaError_t e = to_device ? cudaMemcpyAsync(dev + offs[pc.b] + pc.off, pb + at, pc.n, cudaMemcpyHostToDevice, c->stream)
+                                      : cudaMemcpyAsync(pb + at, dev + offs[pc.b] + pc.off, pc.n, cudaMemcpyDeviceToHost, c->stream);
+            if (e != cudaSuccess) return e;
+            at += pc.n;
+        }
+        return cudaEventRecord(c->pin_ev[k % 2], c->stream);
+    };
+    if (to_device) {
+        for (int k = 0; k < nc; ++k) {
+            if (k >= 2) CU(c, cudaEventSynchronize(c->pin_ev[k % 2])); // the buffer's previous chunk has left
+            host_side(k);
+            CU(c, dma(k));
+        }
+        CU(c, cudaEventSynchronize(c->pin_ev[(nc - 1) % 2]));
+        if (nc >= 2) CU(c, cudaEventSynchronize(c->pin_ev[(nc - 2) % 2]));
+    } else {
+        CU(c, dma(0));
+        for (int k = 0; k < nc; ++k) {
+            if (k + 1 < nc) {
+                // buffer (k + 1) % 2 was emptied by host_side(k - 1): safe to refill while chunk k is copied out
+                CU(c, dma(k + 1));
+            }
+            CU(c, cudaEventSynchronize(c->pin_ev[k % 2]));
+            host_side(k);
+        }
+    }
+    return LWSB_OK;
+}
+
 } // namespace
 
 // ============================================================================ library / context
@@ -262,6 +383,10 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
         b->release();
     for (auto &kv : c->twiddles) kv.second.release();
     for (int i = 0; i < 3; ++i) c->raww[i].release();
+    for (int i = 0; i < 2; ++i) {
+        if (c->pin[i]) cudaFreeHost(c->pin[i]);
+        if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int i = 0; i < 3; ++i)
@@ -269,6 +394,22 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
             if (c->evs[i][k]) cudaEventDestroy(c->evs[i][k]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
+    return LWSB_OK;
+}
+
+// pinned (page-locked) host memory for callers that want the DMA engine to reach their buffers directly
+extern "C" int lwsb_host_alloc(unsigned long long bytes, void **out)
+{
+    if (!out) return LWSB_ERR_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, e == cudaErrorMemoryAllocation ? LWSB_ERR_NOMEM : LWSB_ERR_CUDA, cudaGetErrorString(e)); }
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_host_free(void *p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return LWSB_ERR_CUDA; }
     return LWSB_OK;
 }
 
@@ -416,11 +557,12 @@ extern "C" int lwsb_load(lwsb_ctx *c, const void *const *S_in, const int *T, int
     c->hptr.resize(B);
     if (where == LWSB_HOST) {
         CU(c, c->stage.reserve((size_t)bins * sizeof(double2))); // sized for the complex128 output as well
+        std::vector<size_t> offs(B), sizes(B);
         for (int b = 0; b < B; ++b) {
-            char *dst = c->stage.as<char>() + (size_t)binbase[b] * esz;
-            CU(c, cudaMemcpyAsync(dst, S_in[b], (size_t)T[b] * Nreal * esz, cudaMemcpyHostToDevice, c->stream));
-            c->hptr[b] = dst;
+            offs[b] = (size_t)binbase[b] * esz; sizes[b] = (size_t)T[b] * Nreal * esz;
+            c->hptr[b] = c->stage.as<char>() + offs[b];
         }
+        if (int r = staged_copy(c, c->stage.as<char>(), offs, sizes, const_cast<void *const *>(S_in), true)) return r;
     } else {
         for (int b = 0; b < B; ++b) c->hptr[b] = const_cast<void *>(S_in[b]);
     }
@@ -460,12 +602,14 @@ extern "C" int lwsb_store(lwsb_ctx *c, void *const *S_out, int where)
     launch_crop(c->view(), c->dptr.as<void *const>(), c->maxT, c->stream);
     c->launches += 1;
     CU(c, cudaGetLastError());
-    if (where == LWSB_HOST)
+    if (where == LWSB_HOST) {
+        std::vector<size_t> offs(B), sizes(B);
         for (int b = 0; b < B; ++b) {
             if (!S_out[b]) return fail(c, LWSB_ERR_ARG, "NULL output pointer");
-            CU(c, cudaMemcpyAsync(S_out[b], c->hptr[b], (size_t)c->T[b] * c->Nreal * sizeof(double2),
-                                  cudaMemcpyDeviceToHost, c->stream));
+            offs[b] = (size_t)c->binbase[b] * sizeof(double2); sizes[b] = (size_t)c->T[b] * c->Nreal * sizeof(double2);
         }
+        if (int r = staged_copy(c, c->stage.as<char>(), offs, sizes, S_out, false)) return r;
+    }
     CU(c, cudaStreamSynchronize(c->stream));
     return LWSB_OK;
 }

@@ -235,6 +235,28 @@ def test_api_behaviours(gpu):
     assert gpu.lws(512, 100).W.shape == (512, 6, 6)  # per-frequency weights: the *fractionalQ path (test_fractional_*)
 
 
+def test_pageable_buffers_are_staged_in_chunks(gpu):
+    """Pageable host arrays go through the library's two pinned staging buffers in 24 MB chunks (host threads copying one
+    chunk while the DMA engine moves the other): ~100 MB each way, chunk boundaries inside utterances; with thresholds no
+    bin exceeds, batch_lws is the identity, so every byte must come back.  Results are fresh arrays (page-locked memory
+    from the library's pool when large), never aliases of the input."""
+    rng = np.random.default_rng(12)
+    p = gpu.lws(1024, 256)
+    S = rng.standard_normal((20, 628, 513)) + 1j * rng.standard_normal((20, 628, 513))
+    thr = np.full(2, 1e9)
+    Y = p.batch_lws(S, thresholds=thr)
+    assert Y is not S and Y.dtype == np.complex128 and Y.flags.c_contiguous and np.array_equal(Y, S)
+    Ys = p.batch_lws([S[b, : 100 + 25 * b] for b in range(20)], thresholds=thr)   # ragged list, pageable views
+    assert all(np.array_equal(Ys[b], S[b, : 100 + 25 * b]) for b in range(20))
+    Y2 = p.batch_lws(S, thresholds=thr)
+    assert np.array_equal(Y2, S) and not np.shares_memory(Y2, Y)                   # a second result never reuses a live one
+    out = np.empty_like(S)
+    assert p.batch_lws(S, thresholds=thr, out=out) is out and np.array_equal(out, S)
+    del Y, Y2
+    Y3 = p.batch_lws(S[:3], thresholds=np.zeros(2))                               # pooled blocks are reused safely
+    assert np.array_equal(Y3, p.batch_lws(np.ascontiguousarray(S[:3]), thresholds=np.zeros(2)))
+
+
 def test_full_size_properties(gpu):
     """BASELINE.json configs[1] shape (628 x 513, Q = 4, 100 default iterations), 4 utterances:
     size-independent properties instead of an oracle run -- magnitudes preserved, result
