@@ -364,8 +364,7 @@ def run_b200_arm(args):
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()   # every rank watches its own GPU: the slowest rank sets the time
     barrier()
     l0 = ctx.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -383,8 +382,14 @@ def run_b200_arm(args):
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
     dev_ms = ev[0].elapsed_time(ev[1])
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     dev_ms_max = ranks.max(dev_ms)
+    per_rank = [None] * world
+    mine = {"rank": rank, "device_ms_per_step": dev_ms / args.steps, "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}
+    if world > 1:
+        ranks.dist.all_gather_object(per_rank, mine)
+    else:
+        per_rank = [mine]
     bins_all = ranks.sum(bins_rank)  # every rank holds its own utterances (weak scaling)
     value = throughput(bins_all / world, args.steps, world, dev_ms_max * 1e-3)
     work = ctx.last_batch_work() if it > 0 else None
@@ -490,13 +495,60 @@ def run_b200_arm(args):
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
-            "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
+            "clocks": clocks, "per_rank": per_rank, "wall_ms_per_step": wall_ms / args.steps,
             "plan": plan, "cycles_cluster0": cycles,
             "kernel_share_of_step": sum(stages.values()) * args.steps / dev_ms if dev_ms else None,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
     ranks.close()
+    return 0
+
+
+def run_inprocess_arm(args):
+    """--sharding inprocess: ONE process, the product's own multi-GPU path -- lws_b200.lws(..., device=[0 .. N-1]) splits
+    the batch over the GPUs (longest-processing-time-first over frame counts, one host thread and context per device, no
+    collective).  Host numpy in, host numpy out: the number is end to end by construction.  Run as plain
+    `python bench.py --gpus N --sharding inprocess` (not under torchrun)."""
+    import torch
+    import lws_b200
+    name = args.workload
+    idx, B, n, fs, hop, it = WORKLOADS[name]
+    N = args.gpus
+    if torch.cuda.device_count() < N:
+        raise RuntimeError("--gpus %d but %d visible" % (N, torch.cuda.device_count()))
+    thr = thresholds_for(name, args.thresholds)
+    p = make_plugin(lws_b200, name, device=list(range(N)))
+    p0 = make_plugin(lws_b200, name, device=0)
+    x = np.concatenate([signals(name, r) for r in range(N)])     # N * B utterances: the same per-GPU load as the torchrun arm
+    A = np.abs(p0.stft(x[:B]))
+    A = np.concatenate([A] + [np.abs(p0.stft(x[r * B:(r + 1) * B])) for r in range(1, N)])
+    Bn, T, Nreal = A.shape
+    A_pin = torch.from_numpy(A).pin_memory().numpy()
+    Y_pin = torch.empty(A.shape, dtype=torch.complex128).pin_memory().numpy()
+    for _ in range(args.warmup):
+        hot_path(p, name, A_pin, thr, out=Y_pin)
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hot_path(p, name, A_pin, thr, out=Y_pin)
+        chk = float(np.abs(Y_pin[0, 0, 0]))
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    Y1 = hot_path(p0, name, A_pin[:2], thr)                      # sharded result == single-GPU result
+    assert np.array_equal(np.asarray(Y1), Y_pin[:2]) and np.array_equal(hot_path(p0, name, A_pin[-1:], thr)[0], Y_pin[-1])
+    value = Bn * T * Nreal * args.steps / dt
+    launches = sum(lws_b200.api._context(d).launch_count() for d in range(N))
+    line = {"metric": metric_name(name), "value": value, "unit": "bins/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(workload_desc(name, args.thresholds), sharding="in-process: lws_b200.lws(..., device=[0..%d]), "
+                                                "%d utterances split over the GPUs by frames (LPT), one host thread per GPU" % (N - 1, Bn)),
+            "e2e": {"value": value, "unit": "bins/s", "h2d_bytes_per_step": int(A.nbytes), "d2h_bytes_per_step": int(Y_pin.nbytes),
+                    "ms_per_step": 1e3 * dt / args.steps, "api": "lws_b200.lws(..., device=list(range(%d))) through the reference API, pinned host numpy in/out" % N},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "note": "wall-clock around the public call (the path has no device-resident variant); compare with the torchrun arm's e2e"}
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -509,6 +561,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--thresholds", default="default", choices=["default", "zero"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--sharding", default="ranks", choices=["ranks", "inprocess"],
+                    help="ranks: one process per GPU (torchrun, the driver's contract); inprocess: one process, device=[0..N-1]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # ONE JSON line on stdout, whatever the libraries underneath print (NCCL writes its version banner to fd 1): file
@@ -521,7 +575,8 @@ def main():
     buf = io.StringIO()
     sys.stdout = buf
     try:
-        rc = run_reference_arm(args) if args.impl == "reference" else run_b200_arm(args)
+        rc = run_reference_arm(args) if args.impl == "reference" else (
+            run_inprocess_arm(args) if args.sharding == "inprocess" else run_b200_arm(args))
     finally:
         sys.stdout = sys.__stdout__
         sys.stdout.flush()

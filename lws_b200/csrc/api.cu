@@ -631,6 +631,7 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
     // sweeps whose threshold is not below max|S| cannot move a bin (lwslib.cpp:295-296): the strip kernel drops
     // them, and the plan is sized for the number that remain (largest over the batch)
     int active = iterations;
+    double avg_active = 0.0;
     std::vector<int> nact; // sweeps per utterance that can move a bin
     if (!(flags & LWSB_FORCE_GENERIC)) {
         std::vector<double> mean(c->B), mx(c->B);
@@ -644,6 +645,7 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
             for (int i = 0; i < iterations; ++i) n += (thresholds[i] * mean[b] < mx[b]) ? 1 : 0;
             nact[b] = n;
             active = std::max(active, n);
+            avg_active += (double)n / c->B;
         }
         active = std::max(active, 1);
     }
@@ -653,7 +655,7 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
                                     c->tune_smem > 0 ? std::min((size_t)c->tune_smem, c->prop.sharedMemPerBlockOptin)
                                                      : c->prop.sharedMemPerBlockOptin,
                                     c->prop.multiProcessorCount, &pl, c->tune_cluster, c->tune_sweeps, c->tune_lag, c->tune_tm, fold,
-                                    c->tune_block) &&
+                                    c->tune_block, avg_active) &&
                         c->P >= strips_min_pitch(c->Nreal, c->c0);
     if (strips) {
         CU(c, c->status.reserve(256));

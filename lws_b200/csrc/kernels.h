@@ -40,7 +40,8 @@ struct StripPlan {
     int C, NBr, NBV, NS, G, R, pitch, nthreads, smem_bytes, QS, GFAST, TM; // TM: 0 one thread per task, LWSB_VARIANT_TM, LWSB_VARIANT_PAIR + window mode
 };
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
-                 int force_cluster = 0, int max_sweeps = 0, int force_lag = 0, int variant = 0, int fold = 0, int force_block = 0);
+                 int force_cluster = 0, int max_sweeps = 0, int force_lag = 0, int variant = 0, int fold = 0, int force_block = 0,
+                 double avg_iters = 0.0);
 int strips_min_pitch(int Nreal, int c0);
 cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const double *wi_host, int fold,
                                 const double *thr, const double *max_amp, int iters, const StripPlan &pl,

@@ -238,8 +238,9 @@ __global__ void k_debug_fast_math(long long n, unsigned long long seed, unsigned
 // Chooses cluster size, strip width and sweeps per pass.  Returns false when the shape is not
 // served by this kernel (the generic kernel takes over).
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
-                 int force_cluster, int max_sweeps, int force_lag, int variant, int fold, int force_block)
+                 int force_cluster, int max_sweeps, int force_lag, int variant, int fold, int force_block, double avg_iters)
 {
+    if (avg_iters <= 0.0 || avg_iters > iters) avg_iters = iters; // sweeps per utterance that can move a bin: mean over the batch (iters = the largest)
     if (L != SL || !(Q == 2 || Q == 4 || Q == 8) || iters < 1) return false;
     // variant: the pair-split kernel serves the folded Q = 2 / Q = 4 updates and is the default there
     const bool pair_ok = (Q == 2 && fold == LWSB_FOLD_Q2) || (Q == 4 && fold == LWSB_FOLD_Q4);
@@ -287,7 +288,8 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
         const size_t fixed = 64 + 16 + (size_t)(iters + 8) * sizeof(int) + 256 + 256; // flags, sweep list, alignment, static shared memory of the kernel
         if (smem_limit < fixed + rowbytes * 8) continue;
         const int Rmax = (int)((smem_limit - fixed) / (rowbytes + 8));
-        const int ncl = std::max(1, (sm_count * 9 / 10) / C); // GPC packing loses a few SMs to clusters
+        // resident clusters (cudaOccupancyMaxActiveClusters on B200, one CTA per SM): 148 / 74 / 36-37 / 18
+        const int ncl = std::max(1, C <= 2 ? sm_count / C : (C == 4 ? sm_count / C - 1 : sm_count / C));
         // sweep lag: Q frames is the minimum; an odd lag makes the sweep-fastest thread order bank-conflict free
         for (int QS = Q; QS <= Q + 1; ++QS) {
             if (Rmax < 2 * Q + SLEAD + NS) continue;
@@ -337,15 +339,27 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                 // Pair-split: half the instructions per warp and twice the warps.  A pass adds a fixed prologue.
                 const int cwarps = ((pair || duo ? 2 : 1) * lanes_best + 31) / 32;
                 // per-warp cost scales with the terms per bin: 6 (Q = 2), 17 (Q = 4, folded), 74 (Q = 8)
-                const double tscale = Q == 2 ? 0.4 : (Q == 4 ? 1.0 : 10.0); // Q = 8: 74 unfolded terms, block update not software-pipelined (measured 136k cycles per macro-step)
+                // (Q = 8: bin-loop block update with the default-window mask compiled in, measured 46k cycles per macro-step at
+                // 3 warps on BASELINE configs[4]; 84k before, with one branch per term)
+                const double tscale = Q == 2 ? 0.4 : (Q == 4 ? 1.0 : 4.0);
                 const double bscale = SBK / 8.0;
+                // Bank conflicts enter the time weakly: measured on B200 (profiles/r2_strip_experiments.txt) the conflict-free
+                // order (sweep-fastest, odd sweep lag, rotated ring rows: 1.0 instead of ~1.5 cycles per access) is 15 % faster
+                // at cluster 4 with the same sweeps per pass (128 vs 151 ms on BASELINE configs[1]); at cluster 2 it costs two
+                // sweeps per pass and loses.  The stream of a warp is bound by fp64 issue and load latency first.
+                // Effective cycles per macro-step of a launch (kernel time / rounds of work items / steps per item, so the waits
+                // for neighbour strips and for other passes are in it), fitted on BASELINE configs[1] at default and zero
+                // thresholds: cluster 2, 4 warps: 17.2-17.8k; cluster 4, 5 warps: 19.5-20.0k; cluster 8, 4 warps: 19-24k, 6 warps: 36k
+                // (a fifth warp shares a scheduler with another one: the step lasts as long as that scheduler's two streams;
+                // eight strips in lock step wait for one another a lot: profiles/r2_strip_experiments.txt).
                 const double t_step = pair ? (PAIR_T0 - 800.0 + PAIR_T1 * cwarps * (1.0 + PAIR_TF * (f - 1.0))) * bscale + 800.0 + (C > 2 ? 800.0 : 0.0)
-                                           : (9700.0 + 450.0 * cwarps * f + 1400.0 * std::max(0.0, cwarps * f - 5.6)) * tscale * bscale + 800.0 +
-                                                 (C > 2 ? 2000.0 : 0.0) + (C > 4 ? 1500.0 : 0.0);
+                                           : (14700.0 + 500.0 * std::min(cwarps, 4) + 4500.0 * std::max(0, cwarps - 4)) * (1.0 + 0.3 * (f - 1.0)) * tscale * bscale +
+                                                 800.0 + (C > 2 ? 1700.0 : 0.0) + (C > 4 ? 6000.0 : 0.0);
                 // throughput bound, and the critical path of one utterance: its passes run concurrently on different
                 // clusters, each `lag` macro-steps behind the previous one (it reads what that one has written back)
                 const double lag = (double)LAGB * (Q + SLEAD + QS * (G - 1) + PUBLISH_EVERY) + NBV + LAGB + (C - 1) * NBr;
-                const double cost = std::max(std::ceil((double)B * npass / ncl) * (steps * t_step + 60000.0),
+                const double items = (double)B * std::ceil(avg_iters / G); // work items of the launch (one per utterance and pass)
+                const double cost = std::max(std::ceil(items / ncl) * (steps * t_step + 60000.0),
                                              (steps + (npass - 1) * lag) * t_step + 60000.0);
                 if (!found || cost < best) {
                     found = true; best = cost;

@@ -257,7 +257,7 @@ def test_planner_picks_the_measured_best_plans_for_the_baseline_shapes():
     """The cost model was fitted on B200: for BASELINE configs[1] (67 of 100 sweeps can move a bin with
     the default thresholds) and all-active it must land on the plan measured fastest -- cluster 2, 7 sweeps per pass,
     8-bin blocks -- and for configs[4] (Q = 8, 4 utterances per GPU) on cluster 8; 4-bin blocks only on request."""
-    for active in (67, 100):
+    for active in (60, 67, 71, 75, 80, 90, 100):
         pl = _native.debug_plan_strips(513, 4, 5, active, 628, 64)
         assert (pl["cluster"], pl["sweeps_per_pass"], pl["block_bins"], pl["sweep_lag"]) == (2, 7, 8, 4), pl
     pl = _native.debug_plan_strips(1025, 8, 5, 150, 5632, 4)
