@@ -96,6 +96,10 @@ int lwsb_batch(lwsb_ctx *ctx, const double *thresholds, int iterations, int flag
 int lwsb_nofuture(lwsb_ctx *ctx, int which, const double *thresholds, int iterations, int flags);
 int lwsb_online(lwsb_ctx *ctx, const double *thresholds, int iterations, int look_ahead, int flags);
 int lwsb_store(lwsb_ctx *ctx, void *const *S_out, int where);
+/* what happens between two chained reference calls (lws.pyx:256 then 235-240 of the next one): ghost frames become copies of
+ * the UPDATED edge frames, |.| and its mean are recomputed.  Call it between two stages run on the resident batch to get
+ * run_lws (lws.pyx:495-499); lwsb_run_lws does. */
+int lwsb_restage(lwsb_ctx *ctx);
 
 /* ---- one-shot interface: one call == one reference binding call on B utterances --------
  * (host or device buffers in, complex128 out; synchronous on return) */
@@ -111,6 +115,20 @@ int lwsb_online_lws(lwsb_ctx *ctx, const void *const *S_in, void *const *S_out, 
 int lwsb_run_lws(lwsb_ctx *ctx, const void *const *S_in, void *const *S_out, const int *T, int B, int Nreal,
                  int kind, int where, const double *nofuture_thr, int nofuture_it, const double *online_thr,
                  int online_it, int look_ahead, const double *batch_thr, int batch_it, int flags);
+
+/* ---- streaming online_lws (frame in, frame out) --------------------------------------------------
+ * TF_RTISI_LA (lwslib.cpp:1432-1491) is causal: the row updates of frame m read nothing beyond frame m.  A stream is one
+ * growing utterance kept in HBM; lwsb_stream_push appends frames and runs their row updates, after which every frame
+ * older than the last `look_ahead` ones is final (lwsb_stream_frames).  The reference scales the thresholds by the mean
+ * amplitude of the WHOLE utterance (lws.pyx:360-361): a stream takes that number (or the caller's estimate) up front;
+ * given the true mean the frames are bit-identical to lwsb_online_lws on the complete spectrogram.
+ * The three weight sets must have been set; the stream replaces the context's resident batch. */
+int lwsb_stream_begin(lwsb_ctx *ctx, int Nreal, int max_frames, int kind, double mean_amp, const double *thresholds,
+                      int iterations, int look_ahead, int flags);
+int lwsb_stream_push(lwsb_ctx *ctx, const void *frames, int nframes, int where);        /* (nframes, Nreal) of `kind`   */
+int lwsb_stream_frames(const lwsb_ctx *ctx, int *pushed, int *final_frames);            /* frames 0 .. final-1 are final */
+int lwsb_stream_read(lwsb_ctx *ctx, void *out, int first_frame, int nframes, int where); /* complex128 (nframes, Nreal)  */
+int lwsb_stream_end(lwsb_ctx *ctx);                                                      /* returns the frame count; all final */
 
 /* ---- stft / istft (lws.pyx:43-90, 93-137), batched over signals of equal length ---------
  * lwsb_stft : x (B, nsamples) real -> S (B, M, fftsize/2+1) complex128.  Frame m covers the
@@ -138,6 +156,10 @@ int lwsb_istft(lwsb_ctx *ctx, const void *S_in, int B, int M, int Nreal, const d
  *                    consistency_db (host, [B]) is optional: the consistency of the result (below).
  * lwsb_consistency : get_consistency (lws.pyx:140-144) of B spectrograms (B, M, Nreal) complex128:
  *                    20 log10(|S| / |stft(istft(S)) - S|), Frobenius norms, one value per spectrogram (host, [B]). */
+/* lwsb_resident_consistency : the same number for every utterance of the RESIDENT batch as it stands (host, [B]) -- between
+ *                    lwsb_batch calls it gives the per-sweep trace of the metric without moving the batch. */
+int lwsb_resident_consistency(lwsb_ctx *ctx, const double *awin, const double *swin, int nswin, int fshift, int perfectrec,
+                              double *out_db);
 long long lwsb_reconstruct_length(int nsamples, int fsize, int fshift, int perfectrec);
 int lwsb_reconstruct(lwsb_ctx *ctx, const double *x, int B, int nsamples, const double *awin, const double *swin, int fsize,
                      int fshift, int perfectrec, const double *nofuture_thr, int nofuture_it, const double *online_thr,

@@ -14,7 +14,7 @@ __b200_version__ = "2.0"           # this implementation's own
 __reference_version__ = "1.2.8"
 
 from .dsp import (hann, synthwin, extspec, create_weights, build_asymmetric_windows, get_thresholds)  # noqa: F401
-from .api import batch_lws, nofuture_lws, online_lws, lws  # noqa: F401
+from .api import batch_lws, nofuture_lws, online_lws, lws, OnlineStream  # noqa: F401
 
 
 def stft(x, fsize, fshift, awin, fftsize=None, perfectrec=False, **kw):

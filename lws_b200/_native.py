@@ -40,10 +40,16 @@ SIGNATURES = {
     "lwsb_nofuture": (_ci, [_vp, _ci, _dp, _ci, _ci]),
     "lwsb_online": (_ci, [_vp, _dp, _ci, _ci, _ci]),
     "lwsb_store": (_ci, [_vp, _vpp, _ci]),
+    "lwsb_restage": (_ci, [_vp]),
     "lwsb_batch_lws": (_ci, [_vp, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _ci]),
     "lwsb_nofuture_lws": (_ci, [_vp, _ci, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _ci]),
     "lwsb_online_lws": (_ci, [_vp, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _ci, _ci]),
     "lwsb_run_lws": (_ci, [_vp, _vpp, _vpp, _ip, _ci, _ci, _ci, _ci, _dp, _ci, _dp, _ci, _ci, _dp, _ci, _ci]),
+    "lwsb_stream_begin": (_ci, [_vp, _ci, _ci, _ci, _cd, _dp, _ci, _ci, _ci]),
+    "lwsb_stream_push": (_ci, [_vp, _vp, _ci, _ci]),
+    "lwsb_stream_frames": (_ci, [_vp, _ip, _ip]),
+    "lwsb_stream_read": (_ci, [_vp, _vp, _ci, _ci, _ci]),
+    "lwsb_stream_end": (_ci, [_vp]),
     "lwsb_stft_frames": (_ci, [_ci, _ci, _ci, _ci]),
         "lwsb_stft_prepad": (_ci, [_ci, _ci, _ci]),
     "lwsb_stft": (_ci, [_vp, _vp, _ci, _ci, _dp, _ci, _ci, _ci, _ci, _ci, _vp, _ci]),
@@ -51,6 +57,7 @@ SIGNATURES = {
     "lwsb_reconstruct_length": (_ll, [_ci, _ci, _ci, _ci]),
     "lwsb_reconstruct": (_ci, [_vp, _vp, _ci, _ci, _dp, _dp, _ci, _ci, _ci, _dp, _ci, _dp, _ci, _ci, _dp, _ci, _ci, _vp, _ci, _dp]),
     "lwsb_consistency": (_ci, [_vp, _vp, _ci, _ci, _ci, _dp, _dp, _ci, _ci, _ci, _ci, _dp]),
+    "lwsb_resident_consistency": (_ci, [_vp, _dp, _dp, _ci, _ci, _ci, _dp]),
     "lwsb_last_compute_ms": (_ci, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "lwsb_launch_count": (_ll, [_vp]),
     "lwsb_last_stage_ms": (_ci, [_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -198,6 +205,9 @@ class Context(object):
         t, p, n = self._thr(thresholds)
         self._c(lib().lwsb_online(self._h, p, n, int(look_ahead), flags))
 
+    def restage(self):
+        self._c(lib().lwsb_restage(self._h))
+
     def store(self, outs=None):
         if outs is None:
             outs = [np.empty((int(t), self._Nreal), dtype=np.complex128) for t in self._T]
@@ -260,6 +270,29 @@ class Context(object):
         self._c(lib().lwsb_run_lws(self._h, a_in, a_out, T.ctypes.data_as(_ip), len(in_ptrs), int(Nreal), kind, DEVICE,
                                    p1, n1, p2, n2, int(look_ahead), p3, n3, flags))
 
+    # -- streaming online_lws ---------------------------------------------------------------
+    def stream_begin(self, Nreal, max_frames, kind, mean_amp, thresholds, look_ahead, flags=0):
+        t, p, n = self._thr(thresholds)
+        self._c(lib().lwsb_stream_begin(self._h, int(Nreal), int(max_frames), kind, float(mean_amp), p, n, int(look_ahead), flags))
+        self._Nreal = int(Nreal)
+
+    def stream_push(self, frames):
+        """frames: (n, Nreal) C-contiguous float64 / complex128 (the kind the stream was opened with)"""
+        self._c(lib().lwsb_stream_push(self._h, frames.ctypes.data, frames.shape[0], HOST))
+
+    def stream_frames(self):
+        a, b = _ci(0), _ci(0)
+        self._c(lib().lwsb_stream_frames(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def stream_read(self, first, n):
+        out = np.empty((int(n), self._Nreal), dtype=np.complex128)
+        self._c(lib().lwsb_stream_read(self._h, out.ctypes.data, int(first), int(n), HOST))
+        return out
+
+    def stream_end(self):
+        return self._c(lib().lwsb_stream_end(self._h))
+
     # -- transforms -------------------------------------------------------------------------
     def stft(self, x, awin, fsize, fshift, fftsize, perfectrec):
         """x: (B, nsamples) float64 C-contiguous -> (B, M, fftsize//2+1) complex128."""
@@ -308,6 +341,14 @@ class Context(object):
         out = np.empty(B)
         self._c(lib().lwsb_consistency(self._h, S.ctypes.data, B, M, Nreal, _dptr(awin), _dptr(swin), len(swin), fshift,
                                        int(bool(perfectrec)), HOST, _dptr(out)))
+        return out
+
+    def resident_consistency(self, awin, swin, fshift, perfectrec):
+        """(B,) consistency in dB of the resident batch as it stands (between batch() calls: a per-sweep trace)"""
+        awin = np.ascontiguousarray(awin, dtype=np.float64)
+        swin = np.ascontiguousarray(swin, dtype=np.float64)
+        out = np.empty(len(self._T))
+        self._c(lib().lwsb_resident_consistency(self._h, _dptr(awin), _dptr(swin), len(swin), int(fshift), int(bool(perfectrec)), _dptr(out)))
         return out
 
     # -- introspection ----------------------------------------------------------------------

@@ -188,8 +188,63 @@ def _run_sharded(devices, arrs, outs, fn, overlap=False):
         raise errs[0]
 
 
+def _cuda_tensors(S):
+    """torch CUDA tensor(s) in -> (list of 2-D tensors, kind, shape, device index) or None.  An extension:
+    spectrograms that already live in HBM skip PCIe in both directions; the result is a torch tensor on the same GPU."""
+    try:
+        import torch
+    except ImportError:
+        return None
+    items = list(S) if isinstance(S, (list, tuple)) else [S]
+    if not items or not all(torch.is_tensor(t) and t.is_cuda for t in items):
+        return None
+    if isinstance(S, (list, tuple)):
+        ts, shape = items, "list"
+    elif S.dim() == 3:
+        ts, shape = [S[b] for b in range(S.shape[0])], "3d"
+    else:
+        ts, shape = [S], "2d"
+    if any(t.dim() != 2 for t in ts):
+        raise ValueError('expected (T, Nreal) spectrograms')
+    cplx = any(t.is_complex() for t in ts)
+    dt = torch.complex128 if cplx else torch.float64
+    ts = [t.to(dt).contiguous() for t in ts]
+    if len({t.device.index for t in ts}) != 1:
+        raise ValueError('all spectrograms of a batch must be on the same GPU')
+    return ts, (_native.C128 if cplx else _native.F64), shape, ts[0].device.index
+
+
+def _run_cuda(cu, weights, stage):
+    """stage(ctx) on a device-resident batch: load from the tensors' pointers, compute, store into fresh tensors"""
+    import torch
+    ts, kind, shape, dev = cu
+    nreal = ts[0].shape[1]
+    if any(t.shape[1] != nreal for t in ts):
+        raise ValueError('all spectrograms of a batch must have the same number of bins')
+    if nreal % 2 == 0:
+        raise ValueError(_EVEN)
+    if shape == "3d":
+        whole = torch.empty((len(ts),) + tuple(ts[0].shape), dtype=torch.complex128, device=ts[0].device)
+        outs = [whole[b] for b in range(len(ts))]
+    else:
+        whole, outs = None, [torch.empty(tuple(t.shape), dtype=torch.complex128, device=t.device) for t in ts]
+    torch.cuda.current_stream(ts[0].device).synchronize()  # the producers of the inputs have finished
+    ctx = _context(dev)
+    with ctx.lock:
+        for which, Wx in weights:
+            ctx.set_weights(which, Wx)
+        ctx.load_device([t.data_ptr() for t in ts], [t.shape[0] for t in ts], nreal, kind)
+        stage(ctx)
+        ctx.store_device([o.data_ptr() for o in outs])
+    return outs[0] if shape == "2d" else (whole if shape == "3d" else outs)
+
+
 def batch_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=0, out=None):
     """Batch-mode LWS phase reconstruction (lws.pyx:209-258)."""
+    cu = _cuda_tensors(S)
+    if cu is not None:
+        _check_weights(W, use_simplifications)
+        return S if len(thresholds) == 0 else _run_cuda(cu, [(_native.W, W)], lambda ctx: ctx.batch(thresholds, flags))
     if len(thresholds) == 0:
         return _passthrough(S)
     arrs, kind, shape = _as_batch(S)
@@ -207,6 +262,10 @@ def batch_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=
 
 def nofuture_lws(S, W, thresholds, use_simplifications=True, *, device=None, flags=0, out=None):
     """LWS using past frames only, typically for initialisation (lws.pyx:261-311)."""
+    cu = _cuda_tensors(S)
+    if cu is not None:
+        _check_weights(W, use_simplifications)
+        return S if len(thresholds) == 0 else _run_cuda(cu, [(_native.W, W)], lambda ctx: ctx.nofuture(_native.W, thresholds, flags))
     if len(thresholds) == 0:
         return _passthrough(S)
     arrs, kind, shape = _as_batch(S)
@@ -224,6 +283,11 @@ def nofuture_lws(S, W, thresholds, use_simplifications=True, *, device=None, fla
 
 def online_lws(S, W, W_ai, W_af, thresholds, LA, fshift, use_simplifications=True, *, device=None, flags=0, out=None):
     """Online (TF-RTISI-LA) LWS phase reconstruction (lws.pyx:314-375)."""
+    cu = _cuda_tensors(S)
+    if cu is not None:
+        _check_weights(W, use_simplifications)
+        return S if len(thresholds) == 0 else _run_cuda(cu, [(_native.W, W), (_native.W_AI, W_ai), (_native.W_AF, W_af)],
+                                                        lambda ctx: ctx.online(thresholds, int(LA), flags))
     if len(thresholds) == 0:
         return _passthrough(S)
     arrs, kind, shape = _as_batch(S)
@@ -239,6 +303,58 @@ def online_lws(S, W, W_ai, W_af, thresholds, LA, fshift, use_simplifications=Tru
 
     _run_sharded(_devices(device), arrs, outs, fn)
     return _rebuild(outs, shape, out, getattr(outs, 'whole', None))
+
+
+class OnlineStream(object):
+    """Frame-in / frame-out ``online_lws`` (an extension).  TF_RTISI_LA (lwslib.cpp:1432-1491) is causal:
+    the row updates of frame m read nothing beyond frame m, so they run as soon as the frame arrives and frame
+    ``m - look_ahead`` is final once they have.  ``push(frames)`` returns the frames that became final, ``close()`` the rest.
+
+    The reference scales its thresholds by the mean of |S| over the WHOLE utterance (lws.pyx:360-361), which a stream
+    cannot know: ``mean_amp`` is the caller's value or estimate.  With the true mean the concatenated output is
+    bit-identical to ``online_lws`` on the complete spectrogram.  Each stream owns a context (its frames stay in HBM)."""
+
+    def __init__(self, plugin, n_bins, max_frames, mean_amp, iterations=None, thresholds=None, complex_input=False):
+        if iterations is None:
+            iterations = plugin.online_iterations
+        if thresholds is None:
+            thresholds = get_thresholds(iterations, plugin.online_alpha, plugin.online_beta, plugin.online_gamma)
+        if len(thresholds) == 0:
+            raise ValueError('a stream needs at least one online iteration')
+        if n_bins % 2 == 0:
+            raise ValueError(_EVEN)
+        _check_weights(plugin.W, plugin.use_simplifications)
+        self._kind = _native.C128 if complex_input else _native.F64
+        self._dtype = np.complex128 if complex_input else np.float64
+        self._n_bins = int(n_bins)
+        self._ctx = _native.Context(_devices(plugin.device)[0])
+        self._ctx.set_weights(_native.W, plugin.W)
+        self._ctx.set_weights(_native.W_AI, plugin.W_ai)
+        self._ctx.set_weights(_native.W_AF, plugin.W_af)
+        self._ctx.stream_begin(n_bins, max_frames, self._kind, mean_amp, thresholds, plugin.look_ahead)
+        self._given = 0
+
+    def push(self, frames):
+        """append frames (n, n_bins); returns the (k, n_bins) complex128 frames that are final now (k may be 0)"""
+        f = np.ascontiguousarray(np.atleast_2d(frames), dtype=self._dtype)
+        if f.ndim != 2 or f.shape[1] != self._n_bins:
+            raise ValueError('expected frames of %d bins' % self._n_bins)
+        if f.shape[0]:
+            self._ctx.stream_push(f)
+        return self._take()
+
+    def _take(self):
+        _, final = self._ctx.stream_frames()
+        out = self._ctx.stream_read(self._given, final - self._given)
+        self._given = final
+        return out
+
+    def close(self):
+        """end of the utterance: the last look_ahead frames are final as they stand"""
+        self._ctx.stream_end()
+        out = self._take()
+        self._ctx.close()
+        return out
 
 
 class lws(object):
@@ -385,6 +501,10 @@ class lws(object):
         return online_lws(S, self.W, self.W_ai, self.W_af, thresholds, self.look_ahead, self.fshift,
                           use_simplifications=self.use_simplifications, device=self.device, out=out)
 
+    def online_stream(self, n_bins, max_frames, mean_amp, iterations=None, thresholds=None, complex_input=False):
+        """frame-in / frame-out online_lws with this object's windows and schedule (see OnlineStream)"""
+        return OnlineStream(self, n_bins, max_frames, mean_amp, iterations, thresholds, complex_input)
+
     def batch_lws(self, S, iterations=None, thresholds=None, *, out=None):
         if iterations is None:
             iterations = self.batch_iterations
@@ -392,12 +512,58 @@ class lws(object):
             thresholds = get_thresholds(iterations, self.batch_alpha, self.batch_beta, self.batch_gamma)
         return batch_lws(S, self.W, thresholds, use_simplifications=self.use_simplifications, device=self.device, out=out)
 
+    def batch_lws_trace(self, S, iterations=None, thresholds=None, every=1):
+        """batch_lws with the consistency (dB, lws.pyx:140-144) recorded every `every` sweeps, computed on the device without
+        moving the batch (an extension).  Returns (result, trace): the result is bit-identical to
+        batch_lws(S), trace[k] holds the consistency of every utterance after sweep min((k + 1) * every, iterations), and
+        trace[-1] that of the result -- shape (n_points,) for one spectrogram, (n_points, B) for a batch."""
+        if iterations is None:
+            iterations = self.batch_iterations
+        if thresholds is None:
+            thresholds = get_thresholds(iterations, self.batch_alpha, self.batch_beta, self.batch_gamma)
+        thresholds = np.asarray(thresholds, dtype=np.float64)
+        if len(thresholds) == 0:
+            return _passthrough(S), np.zeros((0,))
+        arrs, kind, shape = _as_batch(S)
+        _check_shapes(arrs)
+        _check_weights(self.W, self.use_simplifications)
+        if 2 * (arrs[0].shape[1] - 1) != self.fsize:
+            raise ValueError('the consistency needs spectrograms of this object\'s frame size')
+        outs = _alloc_outs(arrs, shape)
+        ctx = _context(_devices(self.device)[0])
+        trace = []
+        with ctx.lock:
+            ctx.set_weights(_native.W, self.W)
+            ctx.load(arrs, kind)
+            for i in range(0, len(thresholds), max(1, int(every))):
+                ctx.batch(thresholds[i:i + max(1, int(every))])
+                trace.append(ctx.resident_consistency(self.awin, self.swin, self.fshift, self.perfectrec is True))
+            ctx.store(outs)
+        trace = np.array(trace)
+        return _rebuild(outs, shape, None, getattr(outs, 'whole', None)), (trace[:, 0] if shape == "2d" else trace)
+
     def run_lws(self, S, *, out=None):
         """nofuture -> online -> batch (lws.pyx:495-499), fused on the device: the spectrograms
         cross PCIe once in each direction instead of three times."""
         nf = get_thresholds(self.nofuture_iterations, self.nofuture_alpha, self.nofuture_beta, self.nofuture_gamma)
         on = get_thresholds(self.online_iterations, self.online_alpha, self.online_beta, self.online_gamma)
         ba = get_thresholds(self.batch_iterations, self.batch_alpha, self.batch_beta, self.batch_gamma)
+        cu = _cuda_tensors(S)
+        if cu is not None:  # torch CUDA tensors: the three stages on the device-resident batch, no PCIe traffic
+            _check_weights(self.W, self.use_simplifications)
+            if len(nf) + len(on) + len(ba) == 0:
+                return S
+
+            def stages(ctx):
+                dirty = False
+                for n, fn in ((len(nf), lambda: ctx.nofuture(_native.W_AI, nf)), (len(on), lambda: ctx.online(on, self.look_ahead)),
+                              (len(ba), lambda: ctx.batch(ba))):
+                    if n:
+                        if dirty:
+                            ctx.restage()
+                        fn()
+                        dirty = True
+            return _run_cuda(cu, [(_native.W, self.W), (_native.W_AI, self.W_ai), (_native.W_AF, self.W_af)], stages)
         if len(nf) + len(on) + len(ba) == 0:
             return _passthrough(S)
         arrs, kind, shape = _as_batch(S)

@@ -136,6 +136,10 @@ struct lwsb_ctx {
     int tune_tm = 0;                       // tensor-memory producer/consumer kernel (env LWSB_STRIP_TM=1, lwsb_set_tuning2);
                                            // off by default: measured slower than the single-warp pipeline
     StripPlan last_plan{};
+    // streaming online_lws (lwsb_stream_*): the resident "batch" is one growing utterance
+    bool stream_on = false, stream_ended = false;
+    int stream_cap = 0, stream_kind = 0, stream_iters = 0, stream_LA = 0, stream_flags = 0;
+    DevBuf sthr, sframes;
     std::map<int, DevBuf> twiddles;        // exp(-2 pi i j / N) tables by N
     std::vector<void *> hptr;
 
@@ -378,7 +382,7 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
     CHECK_CTX(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->rx, &c->rS, &c->rR, &c->ry, &c->rn, &c->items, &c->done, &c->trace, &c->E, &c->A, &c->row_max, &c->leaf_tab, &c->tab_of, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
+    for (DevBuf *b : {&c->sthr, &c->sframes, &c->rx, &c->rS, &c->rR, &c->ry, &c->rn, &c->items, &c->done, &c->trace, &c->E, &c->A, &c->row_max, &c->leaf_tab, &c->tab_of, &c->leaf_sum, &c->mean_amp, &c->max_amp, &c->dT,
                       &c->drowbase, &c->stage, &c->dptr, &c->dthr, &c->flags, &c->fx, &c->fS, &c->fwin, &c->fframes, &c->status})
         b->release();
     for (auto &kv : c->twiddles) kv.second.release();
@@ -507,6 +511,7 @@ extern "C" int lwsb_load(lwsb_ctx *c, const void *const *S_in, const int *T, int
         return fail(c, LWSB_ERR_ARG, "per-frequency weights need one row per FFT bin: Qprime == 2 * (Nreal - 1)");
     if (int r = use_device(c)) return r;
     c->B = 0; // invalid until everything below succeeded
+    c->stream_on = false;
     c->stage_valid[0] = c->stage_valid[1] = c->stage_valid[2] = false;
     const int Q = c->w[LWSB_W].Q, L = c->w[LWSB_W].L;
     const int Np = Nreal + 2 * L;
@@ -782,6 +787,122 @@ extern "C" int lwsb_online(lwsb_ctx *c, const double *thresholds, int iterations
     return LWSB_OK;
 }
 
+
+// ============================================================================ streaming online_lws
+// TF_RTISI_LA is causal (lwslib.cpp:1432-1491): the row updates of frame m -- its initial estimate, then `iterations` times
+// [the look-ahead frames m-LA .. m-1, frame m] -- read nothing beyond frame m, so they can run as soon as frame m has
+// arrived, and frame m - LA is final once they have.  A stream is one growing utterance resident in HBM; every push runs
+// the chain positions of the new frames (the generic chain kernel on a range of positions).  Given the same mean amplitude
+// (the reference scales the thresholds by the mean of |S| over the WHOLE utterance, lws.pyx:360-361: a stream needs it --
+// or an estimate -- up front) the frames are bit-identical to online_lws on the complete spectrogram.
+extern "C" int lwsb_stream_begin(lwsb_ctx *c, int Nreal, int max_frames, int kind, double mean_amp, const double *thresholds,
+                                 int iterations, int look_ahead, int flags)
+{
+    CHECK_CTX(c);
+    if (Nreal < 1 || max_frames < 1 || (kind != LWSB_C128 && kind != LWSB_F64) || iterations < 1 || !thresholds || look_ahead < 0)
+        return fail(c, LWSB_ERR_ARG, "bad lwsb_stream_begin arguments");
+    if (Nreal % 2 == 0)
+        return fail(c, LWSB_ERR_EVEN_NREAL, "Please only include non-negative frequencies in the input spectrogram.");
+    for (int i = 0; i < 3; ++i)
+        if (!c->w[i].valid() || c->w[i].Q != c->w[0].Q || c->w[i].L != c->w[0].L || c->w[i].Qp != c->w[0].Qp)
+            return fail(c, LWSB_ERR_STATE, "online mode needs W, W_ai and W_af of the same shape");
+    if (Nreal <= c->w[0].L) return fail(c, LWSB_ERR_UNSUPPORTED, "spectrum narrower than the stencil reach (Nreal <= L) is not supported");
+    if (c->fractional() && c->w[0].Qp != 2 * (Nreal - 1))
+        return fail(c, LWSB_ERR_ARG, "per-frequency weights need one row per FFT bin: Qprime == 2 * (Nreal - 1)");
+    if (Nreal > online_generic_max_nreal(c->w[0].L)) return fail(c, LWSB_ERR_UNSUPPORTED, "spectrum too wide for the online kernel");
+    if (int r = use_device(c)) return r;
+    c->B = 0; c->stream_on = false;
+    const int Q = c->w[0].Q, L = c->w[0].L;
+    const int Np = Nreal + 2 * L, coff = (4 - L % 4) % 4;
+    const int P = (std::max(coff + Np, strips_min_pitch(Nreal, coff + L)) + 3) / 4 * 4;
+    const long long rows = (long long)max_frames + 2 * (Q - 1);
+    CU(c, c->E.reserve((size_t)rows * P * sizeof(double2)));
+    CU(c, c->A.reserve((size_t)rows * P * sizeof(double)));
+    CU(c, c->mean_amp.reserve(sizeof(double)));
+    CU(c, c->max_amp.reserve(sizeof(double)));
+    CU(c, c->dT.reserve(sizeof(int)));
+    CU(c, c->drowbase.reserve(sizeof(long long)));
+    CU(c, c->sthr.reserve((size_t)iterations * sizeof(double)));
+    const long long zero = 0;
+    const int t0 = 0;
+    CU(c, cudaMemcpyAsync(c->drowbase.p, &zero, sizeof zero, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->dT.p, &t0, sizeof t0, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->mean_amp.p, &mean_amp, sizeof mean_amp, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->sthr.p, thresholds, (size_t)iterations * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->T.assign(1, 0); c->rowbase.assign(1, 0); c->binbase.assign(1, 0);
+    c->Nreal = Nreal; c->Q = Q; c->L = L; c->P = P; c->c0 = coff + L; c->maxT = 0;
+    c->total_rows = rows; c->total_bins = 0;
+    c->B = 1;
+    c->stream_on = true; c->stream_ended = false;
+    c->stream_cap = max_frames; c->stream_kind = kind; c->stream_iters = iterations; c->stream_LA = look_ahead;
+    c->stream_flags = flags | (c->fractional() ? LWSB_FRACTIONAL : 0);
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_stream_push(lwsb_ctx *c, const void *frames, int nframes, int where)
+{
+    CHECK_CTX(c);
+    if (!c->stream_on || c->stream_ended) return fail(c, LWSB_ERR_STATE, "no open stream (call lwsb_stream_begin first)");
+    if (!frames || nframes < 1 || (where != LWSB_HOST && where != LWSB_DEVICE)) return fail(c, LWSB_ERR_ARG, "bad lwsb_stream_push arguments");
+    const int T0 = c->T[0], T1 = T0 + nframes;
+    if (T1 > c->stream_cap) return fail(c, LWSB_ERR_ARG, "stream is longer than the max_frames it was opened with");
+    if (int r = use_device(c)) return r;
+    const size_t esz = c->stream_kind == LWSB_C128 ? sizeof(double2) : sizeof(double);
+    const size_t bytes = (size_t)nframes * c->Nreal * esz;
+    const void *src = frames;
+    if (where == LWSB_HOST) {
+        CU(c, c->sframes.reserve(bytes));
+        std::vector<size_t> offs(1, 0), sizes(1, bytes);
+        void *hp[1] = {const_cast<void *>(frames)};
+        if (int r = staged_copy(c, c->sframes.as<char>(), offs, sizes, hp, true)) return r;
+        src = c->sframes.p;
+    }
+    launch_stream_extend(c->view(), c->stream_kind, src, T0, nframes, c->stream);
+    CU(c, cudaMemcpyAsync(c->dT.p, &T1, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const LwsbW w3[3] = {c->devw(LWSB_W), c->devw(LWSB_W_AI), c->devw(LWSB_W_AF)};
+    if (int r = begin_compute(c, 1)) return r;
+    launch_online_generic(c->view(), w3, fold_for(c->Q, c->stream_flags), c->sthr.as<const double>(), c->stream_iters, c->stream_LA, c->stream,
+                          lwsb_online_chain_len(T0, c->stream_iters, c->stream_LA), lwsb_online_chain_len(T1, c->stream_iters, c->stream_LA));
+    c->launches += 2;
+    if (int r = end_compute(c)) return r;
+    CU(c, cudaStreamSynchronize(c->stream)); // T1 (a stack variable) has been read; the caller may reuse `frames`
+    c->T[0] = T1; c->maxT = T1; c->total_bins = (long long)T1 * c->Nreal;
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_stream_frames(const lwsb_ctx *c, int *pushed, int *final_frames)
+{
+    if (!c || !c->stream_on) return LWSB_ERR_STATE;
+    const int T = c->T[0];
+    if (pushed) *pushed = T;
+    if (final_frames) *final_frames = c->stream_ended ? T : std::max(0, T - c->stream_LA);
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_stream_read(lwsb_ctx *c, void *out, int first_frame, int nframes, int where)
+{
+    CHECK_CTX(c);
+    if (!c->stream_on) return fail(c, LWSB_ERR_STATE, "no stream");
+    if (!out || first_frame < 0 || nframes < 0 || first_frame + nframes > c->T[0] || (where != LWSB_HOST && where != LWSB_DEVICE))
+        return fail(c, LWSB_ERR_ARG, "bad lwsb_stream_read arguments");
+    if (nframes == 0) return LWSB_OK;
+    if (int r = use_device(c)) return r;
+    const double2 *src = c->E.as<double2>() + (long long)(first_frame + c->Q - 1) * c->P + c->c0;
+    CU(c, cudaMemcpy2DAsync(out, (size_t)c->Nreal * sizeof(double2), src, (size_t)c->P * sizeof(double2), (size_t)c->Nreal * sizeof(double2),
+                            nframes, where == LWSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LWSB_OK;
+}
+
+extern "C" int lwsb_stream_end(lwsb_ctx *c)
+{
+    CHECK_CTX(c);
+    if (!c->stream_on) return fail(c, LWSB_ERR_STATE, "no stream");
+    c->stream_ended = true; // nothing left to compute: every frame has had its row updates; all frames are final
+    return c->T[0];
+}
+
 // Between two chained stages the reference crops and re-extends (lws.pyx:256 then 235-240 of the
 // next call): ghost frames become copies of the *updated* edge frames, |.| and its mean are
 // recomputed from the updated values.
@@ -792,6 +913,14 @@ static int restage(lwsb_ctx *c)
     c->launches += 3;
     CU(c, cudaGetLastError());
     return LWSB_OK;
+}
+
+extern "C" int lwsb_restage(lwsb_ctx *c)
+{
+    CHECK_CTX(c);
+    if (int r = check_resident(c)) return r;
+    if (int r = use_device(c)) return r;
+    return restage(c);
 }
 
 // ============================================================================ one-shot interface
@@ -1046,6 +1175,30 @@ extern "C" int lwsb_consistency(lwsb_ctx *c, const void *S, int B, int M, int Nr
         dS = c->rS.as<double2>();
     }
     return consistency_device(c, dS, B, M, Nreal, awin, swin, nswin, fsize, fshift, perfectrec, out_db);
+}
+
+// consistency (dB) of every utterance of the RESIDENT batch as it stands (between lwsb_batch calls: a per-sweep trace of
+// the reference's only quality metric, lws.pyx:140-144); fftsize = fsize = 2 (Nreal - 1)
+extern "C" int lwsb_resident_consistency(lwsb_ctx *c, const double *awin, const double *swin, int nswin, int fshift, int perfectrec,
+                                         double *out_db)
+{
+    CHECK_CTX(c);
+    if (!awin || !swin || !out_db || nswin < 1 || fshift < 1) return fail(c, LWSB_ERR_ARG, "bad lwsb_resident_consistency arguments");
+    if (int r = check_resident(c)) return r;
+    if (int r = use_device(c)) return r;
+    const int B = c->B, fsize = 2 * (c->Nreal - 1);
+    CU(c, c->stage.reserve((size_t)c->total_bins * sizeof(double2)));
+    for (int b = 0; b < B; ++b) c->hptr[b] = c->stage.as<double2>() + c->binbase[b];
+    CU(c, cudaMemcpyAsync(c->dptr.p, c->hptr.data(), B * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+    launch_crop(c->view(), c->dptr.as<void *const>(), c->maxT, c->stream);
+    c->launches += 1;
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < B; ++b)
+        if (int r = consistency_device(c, c->stage.as<double2>() + c->binbase[b], 1, c->T[b], c->Nreal, awin, swin, nswin, fsize, fshift,
+                                       perfectrec, out_db + b))
+            return r;
+    return LWSB_OK;
 }
 
 // y = istft(run_lws(|stft(x)|)) for B signals of equal length without leaving the device (lws.pyx:43-137, 495-499 chained)

@@ -26,7 +26,8 @@ void launch_crop(const LwsbView &v, void *const *dst, int maxT, cudaStream_t s);
 void launch_sweeps_generic(const LwsbView &v, const LwsbW &w, int fold, int rframe, int cframe, const double *thr,
                            int iters, cudaStream_t s);
 void launch_online_generic(const LwsbView &v, const LwsbW *w3, int fold, const double *thr, int iters, int LA,
-                           cudaStream_t s);
+                           cudaStream_t s, long long j0 = 0, long long j1 = -1);
+void launch_stream_extend(const LwsbView &v, int kind, const void *src, int m0, int n, cudaStream_t s);
 // kernels_online.cu
 bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const double *const *wi_host, int fold,
                         const double *thr, int iters, int LA, const int *T_host, size_t smem_limit, unsigned *status,

@@ -76,6 +76,44 @@ __global__ void k_extend(LwsbView v, const void *const *src, double *row_max)
     }
 }
 
+// Streaming: the same rows for frames [m0, m0 + n) of utterance 0 as they arrive -- src holds the n new
+// frames -- plus, with the first frame, the Q-1 frozen ghost rows above it (copies of frame 0, lws.pyx:155).  The ghost rows
+// below the last frame are never read by the online chain (every row update uses frames up to the newest one only).
+// grid n (+ Q-1 when m0 == 0)
+template <int KIND>
+__global__ void k_stream_extend(LwsbView v, const void *src, int m0, int n)
+{
+    const int ghosts = m0 == 0 ? v.Q - 1 : 0;
+    const int idx = blockIdx.x;
+    const int f = idx < ghosts ? 0 : idx - ghosts;              // frame inside src
+    const long long row = v.rowbase[0] + (idx < ghosts ? idx : m0 + (v.Q - 1) + f);
+    const int Nreal = v.Nreal, L = v.L;
+    double2 *E = v.E + row * v.P;
+    double *A = v.A + row * v.P;
+    const int e0 = v.c0 - L;
+    for (int x = threadIdx.x; x < v.P; x += blockDim.x) {
+        const int c = x - v.c0;
+        double2 val = make_double2(0.0, 0.0);
+        double a = 0.0;
+        if (x >= e0 && c < Nreal + L) {
+            int cs = c;
+            bool cj = false;
+            if (c < 0) { cs = -c; cj = true; }
+            else if (c >= Nreal) { cs = 2 * (Nreal - 1) - c; cj = true; }
+            if (KIND == 0) {
+                val = reinterpret_cast<const double2 *>(src)[(long long)f * Nreal + cs];
+                a = x_cabs(val.x, val.y);
+            } else {
+                val = make_double2(reinterpret_cast<const double *>(src)[(long long)f * Nreal + cs], 0.0);
+                a = fabs(val.x);
+            }
+            if (cj) val.y = -val.y;
+        }
+        E[x] = val;
+        A[x] = a;
+    }
+}
+
 // mean / max of |S| over the un-extended spectrogram (lws.pyx:240); grid B.
 // `mean_amp = np.mean(np.abs(S))` is numpy's *pairwise* summation of the row-major flattened
 // array (numpy/_core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum: blocks of <= 128
@@ -269,26 +307,29 @@ k_sweeps_generic(LwsbView v, LwsbW w, int fold, int rframe, int cframe, const do
 // ------------------------------------------------------------------------------------------
 // online (TF-RTISI-LA) chain: row update j of the chain, bin c runs at step c + (L+1)*j.
 // One CTA per utterance; thread k serves the chain positions j == k (mod blockDim).
+// [j0, j1) restricts the launch to a range of chain positions (streaming: the positions of the frames just pushed; the
+// earlier ones are complete, the later ones have not begun); j1 < 0 = the whole chain of the utterance's T frames.
 __global__ void __launch_bounds__(1024)
-k_online_generic(LwsbView v, LwsbW w0, LwsbW w_ai, LwsbW w_af, int fold, const double *thresholds, int iters, int LA)
+k_online_generic(LwsbView v, LwsbW w0, LwsbW w_ai, LwsbW w_af, int fold, const double *thresholds, int iters, int LA,
+                 long long j0, long long j1)
 {
     const int u = blockIdx.x;
     const int T = v.T[u], Q = v.Q, Nreal = v.Nreal;
     const int S = v.L + 1;
     const long long base = v.rowbase[u];
     const double mean = v.mean_amp[u];
-    const long long n = lwsb_online_chain_len(T, iters, LA);
+    const long long n = j1 >= 0 ? j1 : lwsb_online_chain_len(T, iters, LA);
     const long long tmax = S * (n - 1) + (Nreal - 1);
     const int nt = blockDim.x; // >= ceil(Nreal / S) + 1 (launch_online_generic guarantees)
     long long jc = -1;
     LwsbOnlineTask task;
     double thr = 0.0;
-    for (long long t = 0; t <= tmax; ++t) {
+    for (long long t = S * j0; t <= tmax; ++t) {
         const long long jhi = t / S;
         // the unique j <= jhi with j == tid (mod nt) and j > jhi - nt
         const long long d = (jhi - threadIdx.x) % nt;
         const long long j = jhi - (d < 0 ? d + nt : d);
-        if (j >= 0 && j < n) {
+        if (j >= j0 && j < n) {
             const long long c = t - S * j;
             if (c < Nreal) {
                 if (j != jc) {
@@ -454,11 +495,18 @@ void launch_sweeps_generic(const LwsbView &v, const LwsbW &w, int fold, int rfra
 }
 
 void launch_online_generic(const LwsbView &v, const LwsbW *w3, int fold, const double *thr, int iters, int LA,
-                           cudaStream_t s)
+                           cudaStream_t s, long long j0, long long j1)
 {
     int nt = (v.Nreal + v.L) / (v.L + 1) + 1;
     nt = (nt + 31) / 32 * 32;
-    k_online_generic<<<v.B, nt, 0, s>>>(v, w3[0], w3[1], w3[2], fold, thr, iters, LA);
+    k_online_generic<<<v.B, nt, 0, s>>>(v, w3[0], w3[1], w3[2], fold, thr, iters, LA, j0, j1);
+}
+
+void launch_stream_extend(const LwsbView &v, int kind, const void *src, int m0, int n, cudaStream_t s)
+{
+    const int grid = n + (m0 == 0 ? v.Q - 1 : 0);
+    if (kind == 0) k_stream_extend<0><<<grid, 256, 0, s>>>(v, src, m0, n);
+    else k_stream_extend<1><<<grid, 256, 0, s>>>(v, src, m0, n);
 }
 
 void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, int iters, cudaStream_t s)

@@ -316,6 +316,37 @@ def test_online_ring_kernels(gpu, oracle, fs, hop, la, its, n):
         _close(pg.online_lws(As[0][:T]), po.online_lws(As[0][:T]), "online T=%d" % T)
 
 
+@pytest.mark.parametrize("fs,hop,kw,chunks", [(512, 128, {}, (1, 2, 3, 5, 8, 13, 40)), (64, 16, {"look_ahead": 0}, (7,)), (64, 8, {"look_ahead": 2}, (1, 30)),
+                                              (128, 64, {"look_ahead": 5}, (4, 1, 1, 9)), (64, 20, {}, (3, 11))])
+def test_streaming_online_equals_offline(gpu, oracle, fs, hop, kw, chunks):
+    """Frame-in / frame-out online_lws (lwsb_stream_*): frames pushed in chunks of any size, every frame returned as soon as it is
+    final (look_ahead frames behind the newest); given the utterance's mean amplitude the concatenation is bit-identical
+    to online_lws on the complete spectrogram -- oracle and offline CUDA path alike (incl. the per-frequency-weights path)."""
+    po, pg = oracle.lws(fs, hop, mode="music", **kw), gpu.lws(fs, hop, mode="music", **kw)
+    A = np.abs(po.stft(make_signal("tonal", 61, 9000)))
+    T = A.shape[0]
+    want = po.online_lws(A)
+    st = pg.online_stream(A.shape[1], max_frames=T, mean_amp=float(np.mean(A)))
+    got, m, i, lat = [], 0, 0, []
+    while m < T:
+        n = min(chunks[i % len(chunks)], T - m)
+        out = st.push(A[m:m + n])
+        m += n; i += 1
+        got.append(out)
+        lat.append(m - sum(len(g) for g in got))
+    assert max(lat) <= pg.look_ahead and all(len(g) <= max(chunks) + pg.look_ahead for g in got)
+    got.append(st.close())
+    Y = np.concatenate(got)
+    _close(Y, want, "streamed online_lws")
+    assert np.array_equal(Y, pg.online_lws(A))
+    # complex input, and an estimate of the mean instead of the true one: still a valid reconstruction of the magnitudes
+    st = pg.online_stream(A.shape[1], max_frames=T, mean_amp=1.1 * float(np.mean(A)), complex_input=True)
+    Z = np.concatenate([st.push(A[:T // 2].astype(np.complex128)), st.push(A[T // 2:].astype(np.complex128)), st.close()])
+    assert Z.shape == want.shape and np.allclose(np.abs(Z), A, rtol=1e-10, atol=1e-12 * A.max())
+    with pytest.raises(ValueError):
+        pg.online_stream(A.shape[1], max_frames=4, mean_amp=1.0).push(A[:5])
+
+
 def test_q8_large_frame_vs_oracle(gpu, oracle):
     """configs[4] geometry (2048-pt, hop 256, Q = 8) at reduced length and 10 iterations."""
     po, pg = oracle.lws(2048, 256), gpu.lws(2048, 256)
@@ -624,6 +655,44 @@ def test_reconstruct_equals_the_chained_calls(gpu, oracle, fs, hop, mode, perfec
             assert np.abs(y[b] - want).max() <= 1e-8 * max(1.0, np.abs(want).max())
     y1 = pg.reconstruct(x[0])
     assert y1.shape == y[0].shape and np.array_equal(y1, y[0])
+
+
+def test_per_sweep_consistency_trace(gpu, oracle):
+    """batch_lws_trace: the consistency after every k-th sweep, computed on the resident batch between staged lwsb_batch calls;
+    the result equals batch_lws (ghost frames stay frozen across the calls), the trace equals the oracle's consistency of the
+    oracle's partial results."""
+    po, pg = oracle.lws(512, 128, batch_alpha=2), gpu.lws(512, 128, batch_alpha=2)
+    As = [np.abs(po.stft(make_signal(k, 80 + i, 6000))) for i, k in enumerate(("tonal", "white"))]
+    thr = gpu.get_thresholds(12, 2, 0.1, 1)
+    Y, tr = pg.batch_lws_trace(As[0], thresholds=thr, every=4)
+    _close(Y, po.batch_lws(As[0], thresholds=thr), "traced batch_lws")
+    assert tr.shape == (3,) and tr[0] < tr[-1]
+    for k in range(3):
+        assert abs(tr[k] - po.get_consistency(po.batch_lws(As[0], thresholds=thr[:4 * (k + 1)]))) < 1e-7
+    Yb, trb = pg.batch_lws_trace(np.stack([As[0], As[1]]), iterations=6, every=1)
+    assert trb.shape == (6, 2) and np.array_equal(Yb, pg.batch_lws(np.stack([As[0], As[1]]), iterations=6))
+
+
+def test_cuda_tensors_in_and_out(gpu, oracle):
+    """torch CUDA tensors in -> torch CUDA tensors out (complex128, same GPU), nothing crosses PCIe; same bits as the host path."""
+    import torch
+    po, pg = oracle.lws(512, 128, mode="music", batch_iterations=10, batch_alpha=2), gpu.lws(512, 128, mode="music", batch_iterations=10, batch_alpha=2)
+    A = np.abs(po.stft(make_signal("tonal", 90, 9000)))
+    At = torch.from_numpy(A).cuda()
+    Y = pg.batch_lws(At)
+    assert torch.is_tensor(Y) and Y.is_cuda and Y.dtype == torch.complex128 and Y.shape == At.shape
+    _close(Y.cpu().numpy(), po.batch_lws(A), "batch_lws on a CUDA tensor")
+    _close(pg.run_lws(At).cpu().numpy(), po.run_lws(A), "run_lws on a CUDA tensor")
+    _close(pg.online_lws(At).cpu().numpy(), po.online_lws(A), "online_lws on a CUDA tensor")
+    _close(pg.nofuture_lws(At.to(torch.complex128)).cpu().numpy(), po.nofuture_lws(A), "nofuture_lws on a complex CUDA tensor")
+    B3 = torch.stack([At[:30], At[30:60]])
+    Y3 = pg.batch_lws(B3)
+    assert Y3.shape == B3.shape and np.array_equal(Y3[1].cpu().numpy(), pg.batch_lws(A[30:60]))
+    Yl = pg.batch_lws([At[:30], At[:55]])
+    assert isinstance(Yl, list) and np.array_equal(Yl[1].cpu().numpy(), pg.batch_lws(A[:55]))
+    assert pg.batch_lws(At, iterations=0) is At
+    with pytest.raises(ValueError):
+        pg.batch_lws(At[:, :-1])
 
 
 def test_consistency_on_device(gpu, oracle):
