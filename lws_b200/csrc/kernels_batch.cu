@@ -250,7 +250,7 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
     if (var == LWSB_VARIANT_AUTO) var = LWSB_VARIANT_SCALAR;
     if (var == LWSB_VARIANT_DUO && !pair_ok) var = LWSB_VARIANT_SCALAR; // two lanes per task: the folded Q = 2 / Q = 4 updates
 #ifndef LWSB_EXPERIMENTS
-    if (var == LWSB_VARIANT_TM || var >= LWSB_VARIANT_PAIR) var = LWSB_VARIANT_SCALAR;
+    if (var == LWSB_VARIANT_TM || var == LWSB_VARIANT_DUO || var >= LWSB_VARIANT_PAIR) var = LWSB_VARIANT_SCALAR;
 #endif
     if (var >= LWSB_VARIANT_PAIR && (!pair_ok || var > LWSB_VARIANT_PAIR + 5)) var = LWSB_VARIANT_SCALAR;
 #ifndef LWSB_PAIR_EXPERIMENTS

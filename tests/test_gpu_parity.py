@@ -431,6 +431,7 @@ DUO_CASES = [  # fsize, hop, samples, iterations, cluster, sweeps per pass, swee
 ]
 
 
+@needs_experiments
 @pytest.mark.parametrize("fs,hop,n,its,cluster,sweeps,lag", DUO_CASES, ids=["%d-%d-n%d-it%d-C%d-G%d-lag%d" % c for c in DUO_CASES])
 def test_strip_kernel_two_lanes_per_task(gpu, oracle, fs, hop, n, its, cluster, sweeps, lag):
     """The two-lanes-per-task kernel (lane l of warp w takes the even bins of a block, lane l of warp w + NWT the odd
@@ -524,8 +525,8 @@ def test_strip_kernel_variants(gpu, oracle, variant, fs, hop, n, its, cluster, l
     kernels (10 + window mode + 3 * explicit pipelining; modes that are not compiled into this build fall back to the
     default one): same bits, default and custom windows."""
     from lws_b200 import api
-    if variant >= 10 and not _experiments():
-        pytest.skip("pair-split kernels are built only with -DLWSB_EXPERIMENTS")
+    if variant >= 3 and not _experiments():
+        pytest.skip("the two-lane and pair-split kernels are built only with -DLWSB_EXPERIMENTS")
     ctx = api._context(0)
     po, pg = oracle.lws(fs, hop), gpu.lws(fs, hop)
     A = np.abs(po.stft(make_signal("tonal", 4, n)))
@@ -550,8 +551,8 @@ def test_strip_kernel_variants(gpu, oracle, variant, fs, hop, n, its, cluster, l
 def test_strip_kernel_variants_custom_window_and_complex_input(gpu, oracle, variant):
     """A window whose |W| > 1e-12 mask differs from the default pattern (run-time mask path) and a complex input."""
     from lws_b200 import api
-    if variant >= 10 and not _experiments():
-        pytest.skip("pair-split kernels are built only with -DLWSB_EXPERIMENTS")
+    if variant >= 3 and not _experiments():
+        pytest.skip("the two-lane and pair-split kernels are built only with -DLWSB_EXPERIMENTS")
     ctx = api._context(0)
     g = golden("custom_win")
     case = [c for c in CASES if c["name"] == "custom_win"][0]
