@@ -180,7 +180,7 @@ int lwsb_last_stage_ms(lwsb_ctx *ctx, float *ms3);
  * that can move a bin (threshold below max|S|; the others are dropped before launch), work items, passes} */
 int lwsb_last_batch_work(const lwsb_ctx *ctx, long long *out4);
 /* which kernel the last lwsb_online call ran: 0 generic (global memory), 1 shared-memory ring with one bin per step,
- * 2 ring with two bins per step */
+ * 2 ring with two bins per step and thread, 3 ring with two bins per step on two lanes (env LWSB_ONLINE_DUO=0 selects 2) */
 int lwsb_last_online_kernel(const lwsb_ctx *ctx);
 /* 1 and the plan {cluster size, blocks per strip, virtual blocks, frame slots, sweeps per pass, ring rows,
  * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order, kernel variant, bins per block} (13 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it

@@ -128,7 +128,7 @@ struct lwsb_ctx {
     int trace_items = 0;
     std::vector<int> trace_list;
     int last_kernel = 0;                   // 0 generic, 1 strips (introspection)
-    int last_online_kernel = 0;            // 0 generic, 1 ring (one bin per step), 2 ring (two bins per step)
+    int last_online_kernel = 0;            // 0 generic, 1 ring (one bin per step), 2 ring (two bins per step), 3 ring (two bins per step on two lanes)
     long long tune_smem = 0;               // tuning knobs (lwsb_set_tuning): shared-memory budget, cluster size,
     int tune_cluster = 0, tune_sweeps = 0; // sweeps per pass; 0 = automatic
     int tune_block = 0;                    // bins per block of the strip kernel: 0 automatic, 4 or 8 (env LWSB_STRIP_BLOCK, lwsb_set_block_bins)

@@ -11,6 +11,7 @@
 // One CTA per utterance.  Arithmetic: the reference's, operation for operation (exact.cuh).
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include "exact.cuh"
 #include "kernels.h"
@@ -328,6 +329,201 @@ k_online_ring2(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *t
             for (int x = threadIdx.x; x < Np; x += nt) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
 }
 
+// ---------------------------------------------------------------- two bins per step on two lanes (Q <= 4)
+// k_online_ring2's step is the in-order stream of one thread: term values of bin c0, term values of bin c0 + 1, the
+// order-bound chain of c0 (centre terms, ordered sum, sqrt, division, commit), the chain of c0 + 1 -- ~2 400 instructions at
+// the issue rate of a lone warp (ncu: 26 % issue, fp64 pipe 12 %, shared-memory pipe 2 %: the SM is idle).  Here the two
+// bins of a task go to lane l of warp w (bin c0) and lane l of warp w + NW (bin c0 + 1): the term values of both bins are
+// formed at the same time on different schedulers' slots, then the chain of c0 runs, a named barrier hands the committed
+// bin over (bar.arrive / bar.sync, the producer-consumer idiom of the PTX manual), and the chain of c0 + 1 follows.  Same
+// operations in the same order per bin: same bits.
+__device__ __forceinline__ void online_pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void online_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// values of the centre-frame terms k = K0 .. L of a bin (K0 = 1 for the first bin of a step: every neighbour it reads was
+// committed in an earlier step; K0 = 2 for the second bin, whose k = 1 term reads the bin its partner lane is about to commit)
+struct OnlineCentre { double r[OL], i[OL]; };
+
+template <int Q, int P, int K0>
+__device__ __forceinline__ void online_centre_values(const OnlineRingCell &E, const OnlineW<Q> &w, int ws, OnlineCentre &cv)
+{
+#pragma unroll
+    for (int k = K0; k <= OL; ++k) {
+        const double2 b = E(0, -k), c = E(0, +k);
+        online_value(w.wr[ws][P][0][k], w.wi[ws][P][0][k], b.x, b.y, c.x, c.y, cv.r[k - 1], cv.i[k - 1]);
+    }
+}
+
+// the order-bound part with the centre values of k >= K0 already formed: same additions in the same order as online_accumulate
+template <int Q, int P, int FOLD, int K0>
+__device__ __forceinline__ void online_accumulate_pre(const OnlineRingCell &E, const OnlineW<Q> &w, int ws, int cframe,
+                                                      const OnlineCentre &cv, const OnlineVals<Q, FOLD> &v, double &tr, double &ti)
+{
+    constexpr int PN = (Q - P) % Q;
+    tr = 0.0; ti = 0.0;
+    auto add_if = [&](bool f, double vr, double vi) {
+        const double nr = __dadd_rn(tr, vr), ni = __dadd_rn(ti, vi);
+        tr = f ? nr : tr; ti = f ? ni : ti;
+    };
+    {
+        const unsigned f0 = cframe ? w.flag[ws][P][0] : 0u;
+#pragma unroll
+        for (int k = 1; k <= OL; ++k) {
+            double vr, vi;
+            if (k < K0) {
+                const double2 b = E(0, -k), c = E(0, +k);
+                online_value(w.wr[ws][P][0][k], w.wi[ws][P][0][k], b.x, b.y, c.x, c.y, vr, vi);
+            } else { vr = cv.r[k - 1]; vi = cv.i[k - 1]; }
+            add_if((f0 >> k) & 1u, vr, vi);
+        }
+    }
+    online_for_each_pair<Q, P, FOLD>([&](auto rc, auto, auto basec) {
+        constexpr int r = decltype(rc)::value;
+        constexpr int base = decltype(basec)::value;
+        const unsigned f = w.flag[ws][P][r], fn = w.flag[ws][PN][r];
+        add_if(f & 1u, v.r[base], v.i[base]);
+#pragma unroll
+        for (int k = 1; k <= OL; ++k) {
+            if (FOLD == LWSB_FOLD_ANY) {
+                add_if((f >> k) & 1u, v.r[base + 2 * k - 1], v.i[base + 2 * k - 1]);
+                add_if((fn >> k) & 1u, v.r[base + 2 * k], v.i[base + 2 * k]);
+            } else add_if((f >> k) & 1u, v.r[base + k], v.i[base + k]);
+        }
+    });
+}
+
+template <int Q, int FOLD, int P, int K0>
+__device__ __forceinline__ void online_commit_bin(double2 *ring, int rmask, int pitch, const OnlineW<Q> &w, const LwsbOnlineTask &task,
+                                                  const OnlineRingCell &cell, const OnlineCentre &cv, const OnlineVals<Q, FOLD> &v, int c,
+                                                  int Nreal, double a)
+{
+    constexpr int L = OL;
+    double tr, ti;
+    online_accumulate_pre<Q, P, FOLD, K0>(cell, w, task.which, task.cframe, cv, v, tr, ti);
+    double2 val;
+    if (x_project(tr, ti, a, val)) {
+        double2 *Rrow = ring + (size_t)(task.row & rmask) * pitch;
+        Rrow[L + c] = val;
+        if (c >= 1 && c <= L) Rrow[L - c] = make_double2(val.x, -val.y);
+        else if (c >= Nreal - 1 - L && c <= Nreal - 2) Rrow[L + 2 * (Nreal - 1) - c] = make_double2(val.x, -val.y);
+    }
+}
+
+template <int Q, int FOLD>
+__global__ void __launch_bounds__(256)
+k_online_duo(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *thresholds, int iters, int LA, int R, int pitch,
+             int S, unsigned *status)
+{
+    static_assert(Q <= 4 && Q % 2 == 0, "two bins per step: the first bin of a step has an even residue");
+    extern __shared__ __align__(16) unsigned char online_smem[];
+    double2 *ring = reinterpret_cast<double2 *>(online_smem);
+    __shared__ OnlineW<Q> wsm; // indexed per lane (each lane its own row update): shared memory serves divergent addresses
+    for (int i = threadIdx.x; i < (int)(sizeof(OnlineW<Q>) / 4); i += blockDim.x)
+        reinterpret_cast<unsigned *>(&wsm)[i] = reinterpret_cast<const unsigned *>(&w)[i];
+    __syncthreads();
+    const int u = blockIdx.x;
+    const int T = v.T[u], Nreal = v.Nreal, P = v.P;
+    constexpr int L = OL;
+    const int Np = Nreal + 2 * L, Tp = T + 2 * (Q - 1), rmask = R - 1;
+    double2 *E0 = v.E + v.rowbase[u] * (long long)P + (v.c0 - L); // extended (row 0, column 0)
+    const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
+    const double mean = v.mean_amp[u];
+    const long long n = lwsb_online_chain_len(T, iters, LA);
+    const long long bmax = (long long)S * (n - 1) + (Nreal - 1);
+    const int nall = blockDim.x, nt = nall >> 1;          // nt tasks in flight, two lanes each
+    const int half = threadIdx.x >= nt ? 1 : 0;           // 0: bin c0, 1: bin c0 + 1 (warp-uniform: nt is a multiple of 32)
+    const int tix = threadIdx.x - half * nt;
+    const int bar = 1 + (tix >> 5);                        // named barrier of the warp pair (0 is __syncthreads)
+    int lo = 0, hi = -1; // extended rows [lo, hi] are resident
+    long long jc = -1;
+    LwsbOnlineTask task;
+    task.row = Q - 1; task.which = 0; task.rframe = 1; task.cframe = 0; task.thr = -1;
+    double thr = 0.0, a_next = 0.0;
+    long long d = (nt - tix % nt) % nt;                   // (jhi - tix) mod nt at jhi = 0
+    for (long long bt = 0; bt <= bmax + 1; bt += 2) {
+        if (bt % S == 0) { // the front of the chain moves to a new row update: residency check (uniform across the CTA)
+            const long long jhi = min(bt / S, n - 1);
+            long long jlo = bt < Nreal ? 0 : (bt - (Nreal - 1) + S - 1) / S;
+            if (jlo > n - 1) jlo = n - 1;
+            const int need_hi = min(Tp - 1, lwsb_online_frame(iters, LA, jhi) + 2 * (Q - 1));
+            const int need_lo = max(0, lwsb_online_frame(iters, LA, jlo) - LA);
+            if (need_hi > hi) {
+                if (need_hi - need_lo + 1 > R && threadIdx.x == 0) atomicCAS(status, 0u, 0xE1000000u | (unsigned)u);
+                for (int e = lo; e < need_lo; ++e) // rows the chain has left: back to global memory
+                    if (e >= Q - 1 && e < T + Q - 1)
+                        for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+                lo = need_lo;
+                __syncthreads();
+                for (int e = hi + 1; e <= need_hi; ++e) // rows the chain is about to reach
+                    for (int x = threadIdx.x; x < Np; x += nall) ring[(size_t)(e & rmask) * pitch + x] = E0[(long long)e * P + x];
+                hi = need_hi;
+                __syncthreads();
+            }
+        }
+        // the row update this lane works on: j = jhi - d with d = (jhi - tix) mod nt, kept incrementally (jhi grows by one
+        // every S / 2 steps)
+        if (bt % S == 0 && bt > 0) d = d + 1 == nt ? 0 : d + 1;
+        const long long jhi = bt / S;
+        const long long j = jhi - d;
+        bool act = false;
+        int c = 0;
+        double a = 0.0;
+        if (j >= 0 && j < n) {
+            const int c0 = (int)(bt - (long long)S * j); // even, >= 0
+            c = c0 + half;
+            if (c < Nreal) {
+                if (j != jc) {
+                    jc = j;
+                    task = lwsb_online_decode(T, iters, LA, Q, j);
+                    thr = task.thr < 0 ? 0.0 : __dmul_rn(thresholds[task.thr], mean); // lws.pyx:361, lwslib.cpp:1467
+                    a = __ldg(A0 + (long long)task.row * P + L + c);
+                } else a = a_next;
+                if (c + 2 < Nreal) a_next = __ldg(A0 + (long long)task.row * P + L + c + 2); // this lane's bin of the next step
+                act = a > thr; // lwslib.cpp:295-296
+            }
+        }
+        // this lane's bin: term values first (both lanes of a task at the same time), then the chains in bin order
+        const bool p2 = Q > 2 && (c & 2);                 // residue of the bin: (c mod 4) = half + (p2 ? 2 : 0); Q = 2: half
+        const OnlineRingCell cell{ring, rmask, pitch, task.row, L + c};
+        OnlineVals<Q, FOLD> vals;
+        OnlineCentre cv;
+        if (act) {
+            if (half == 0) {
+                if (!p2) { online_values<Q, 0, FOLD>(cell, wsm, task.which, task.rframe, vals); online_centre_values<Q, 0, 1>(cell, wsm, task.which, cv); }
+                else { online_values<Q, 2 % Q, FOLD>(cell, wsm, task.which, task.rframe, vals); online_centre_values<Q, 2 % Q, 1>(cell, wsm, task.which, cv); }
+            } else {
+                if (!p2) { online_values<Q, 1, FOLD>(cell, wsm, task.which, task.rframe, vals); online_centre_values<Q, 1, 2>(cell, wsm, task.which, cv); }
+                else { online_values<Q, 3 % Q, FOLD>(cell, wsm, task.which, task.rframe, vals); online_centre_values<Q, 3 % Q, 2>(cell, wsm, task.which, cv); }
+            }
+        }
+        if (half == 0) {
+            if (act) {
+                if (!p2) online_commit_bin<Q, FOLD, 0, 1>(ring, rmask, pitch, wsm, task, cell, cv, vals, c, Nreal, a);
+                else online_commit_bin<Q, FOLD, 2 % Q, 1>(ring, rmask, pitch, wsm, task, cell, cv, vals, c, Nreal, a);
+            }
+            __syncwarp();
+            online_pair_arrive(bar);
+        } else {
+            __syncwarp();
+            online_pair_sync(bar);
+            // near the ends of the spectrum a centre neighbour n -+ k, k >= 2, can be the MIRROR cell of the bin the partner
+            // has just committed (bin b's mirror sits at -b, resp. 2 (Nreal - 1) - b): those values are formed again now
+            if (act && (c - 1 <= L || c - 1 >= Nreal - 2 - L)) {
+                if (!p2) online_centre_values<Q, 1, 2>(cell, wsm, task.which, cv);
+                else online_centre_values<Q, 3 % Q, 2>(cell, wsm, task.which, cv);
+            }
+            if (act) {
+                if (!p2) online_commit_bin<Q, FOLD, 1, 2>(ring, rmask, pitch, wsm, task, cell, cv, vals, c, Nreal, a);
+                else online_commit_bin<Q, FOLD, 3 % Q, 2>(ring, rmask, pitch, wsm, task, cell, cv, vals, c, Nreal, a);
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = lo; e <= hi; ++e)
+        if (e >= Q - 1 && e < T + Q - 1)
+            for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+}
+
 template <int Q, int FOLD, int P>
 __device__ __forceinline__ void online_sum_for_residue(int p, const OnlineRingCell &E, const OnlineW<Q> &w, int ws, int rframe,
                                                        int cframe, double &tr, double &ti)
@@ -440,10 +636,21 @@ int online_max_span(int T, int Nreal, int S, int Q, int iters, int LA)
 
 template <int Q, int FOLD>
 cudaError_t launch_t(const LwsbView &v, const OnlineW<Q> &w, const double *thr, int iters, int LA, int R, int pitch, int S, int nt,
-                     size_t bytes, unsigned *status, int *which_kernel, cudaStream_t s)
+                     size_t bytes, size_t smem_limit, unsigned *status, int *which_kernel, cudaStream_t s)
 {
     *which_kernel = 1;
     if constexpr (Q <= 4) {
+        const char *e_duo = getenv("LWSB_ONLINE_DUO");
+        if (S >= 2 + OL && S % 2 == 0 && 2 * nt <= 256 && !(e_duo && atoi(e_duo) == 0)) { // two bins per step on two lanes
+            auto kern3 = k_online_duo<Q, FOLD>;
+            if (bytes > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                if (e != cudaSuccess) return e;
+            }
+            kern3<<<v.B, 2 * nt, bytes, s>>>(v, w, thr, iters, LA, R, pitch, S, status);
+            *which_kernel = 3;
+            return cudaGetLastError();
+        }
         if (S >= 2 + OL && S % 2 == 0) { // two bins per step
             *which_kernel = 2;
             auto kern2 = k_online_ring2<Q, FOLD>;
@@ -466,7 +673,7 @@ cudaError_t launch_t(const LwsbView &v, const OnlineW<Q> &w, const double *thr, 
 
 template <int Q>
 cudaError_t launch_q(const LwsbView &v, const double *const *wr, const double *const *wi, int fold, const double *thr, int iters,
-                     int LA, int R, int pitch, int S, int nt, size_t bytes, unsigned *status, int *which_kernel, cudaStream_t s)
+                     int LA, int R, int pitch, int S, int nt, size_t bytes, size_t smem_limit, unsigned *status, int *which_kernel, cudaStream_t s)
 {
     OnlineW<Q> w;
     for (int ws = 0; ws < 3; ++ws)
@@ -480,9 +687,9 @@ cudaError_t launch_q(const LwsbView &v, const double *const *wr, const double *c
                 }
                 w.flag[ws][p][r] = f;
             }
-    if (fold == LWSB_FOLD_ANY) return launch_t<Q, LWSB_FOLD_ANY>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s);
-    if constexpr (Q == 4) { if (fold == LWSB_FOLD_Q4) return launch_t<4, LWSB_FOLD_Q4>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); }
-    if constexpr (Q == 2) { if (fold == LWSB_FOLD_Q2) return launch_t<2, LWSB_FOLD_Q2>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); }
+    if (fold == LWSB_FOLD_ANY) return launch_t<Q, LWSB_FOLD_ANY>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s);
+    if constexpr (Q == 4) { if (fold == LWSB_FOLD_Q4) return launch_t<4, LWSB_FOLD_Q4>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); }
+    if constexpr (Q == 2) { if (fold == LWSB_FOLD_Q2) return launch_t<2, LWSB_FOLD_Q2>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); }
     return cudaErrorInvalidValue;
 }
 
@@ -513,9 +720,9 @@ bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const d
     nt = (nt + 31) / 32 * 32;
     if (nt > 256) return false;
     switch (Q) {
-    case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); break;
-    case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); break;
-    case 8: *err = launch_q<8>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, status, which_kernel, s); break;
+    case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); break;
+    case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); break;
+    case 8: *err = launch_q<8>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); break;
     }
     return true;
 }

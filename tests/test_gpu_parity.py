@@ -289,7 +289,7 @@ def test_cfg3_cfg4_one_utterance_vs_oracle(gpu, oracle):
     _close(pg.nofuture_lws(A), po.nofuture_lws(A), "cfg3 nofuture")
     _close(pg.online_lws(A), po.online_lws(A), "cfg3 online")
     from lws_b200 import api
-    assert api._context(0).last_online_kernel() == 2
+    assert api._context(0).last_online_kernel() == 3
     _close(pg.run_lws(A), po.run_lws(A), "cfg4 run_lws")
     # a batch of three: every member equals the single-utterance result
     Ys = pg.online_lws(np.stack([A, A[::-1], A]))
@@ -299,8 +299,8 @@ def test_cfg3_cfg4_one_utterance_vs_oracle(gpu, oracle):
 @pytest.mark.parametrize("fs,hop,la,its,n", [(1024, 256, 3, 10, 40000), (512, 128, 3, 4, 9000), (512, 128, 5, 3, 9000), (512, 128, 1, 5, 5000),
                                              (512, 128, 0, 6, 5000), (64, 16, 3, 10, 4000), (128, 64, 1, 7, 6000), (2048, 256, 3, 3, 30000)])
 def test_online_ring_kernels(gpu, oracle, fs, hop, la, its, n):
-    """The shared-memory ring kernel of online_lws (two bins per step) and the generic fallback against the oracle over
-    look-aheads, iteration counts and ragged batches."""
+    """The shared-memory ring kernel of online_lws (two bins per step on two lanes) and the generic fallback against the
+    oracle over look-aheads, iteration counts and ragged batches."""
     from lws_b200 import api
     ctx = api._context(0)
     kw = dict(look_ahead=la, online_iterations=its)
@@ -308,7 +308,7 @@ def test_online_ring_kernels(gpu, oracle, fs, hop, la, its, n):
     As = [np.abs(po.stft(make_signal(k, 31 + i, n + 700 * i))) for i, k in enumerate(("tonal", "white", "tonal"))]
     for thr in (None, np.zeros(its)):
         Ys = pg.online_lws(As, thresholds=thr)
-        want = 0 if fs // hop > 4 else 2  # Q = 8 at 1025 bins: ring too large for shared memory, generic kernel
+        want = 0 if fs // hop > 4 else 3  # Q = 8 at 1025 bins: ring too large for shared memory, generic kernel
         assert ctx.last_online_kernel() == want, ctx.last_online_kernel()
         for A, Y in zip(As, Ys):
             _close(Y, po.online_lws(A, thresholds=thr), "online ring kernel, LA=%d" % la)
