@@ -11,6 +11,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -46,15 +47,19 @@ struct DevBuf {
 // an item's producer -- the previous pass of the same utterance -- always has a smaller index: clusters take items in
 // increasing order, hence the producer is finished or running whenever an item waits for it.  Returns the largest
 // number of passes of any utterance.
-int build_work_items(const int *nact, int B, int G, std::vector<int> &items)
+// `group` > 0 lists the utterances in groups of that many, pass-major inside a group: the groups then finish one after the
+// other and their results can leave the device while the later groups are still being worked on (lwsb_batch_lws).
+int build_work_items(const int *nact, int B, int G, std::vector<int> &items, int group = 0)
 {
     int max_pass = 0;
     items.clear();
-    for (int pass = 0, more = 1; more; ++pass) {
-        more = 0;
-        for (int b = 0; b < B; ++b)
-            if (pass * G < nact[b]) { items.push_back(b); items.push_back(pass); more = 1; max_pass = pass + 1; }
-    }
+    if (group <= 0 || group > B) group = B;
+    for (int g0 = 0; g0 < B; g0 += group)
+        for (int pass = 0, more = 1; more; ++pass) {
+            more = 0;
+            for (int b = g0; b < std::min(B, g0 + group); ++b)
+                if (pass * G < nact[b]) { items.push_back(b); items.push_back(pass); more = 1; max_pass = std::max(max_pass, pass + 1); }
+        }
     return max_pass;
 }
 
@@ -143,6 +148,9 @@ struct lwsb_ctx {
     std::map<int, DevBuf> twiddles;        // exp(-2 pi i j / N) tables by N
     std::vector<void *> hptr;
 
+    cudaStream_t copy_stream = nullptr;    // results leave on it while the strip kernel still runs (lwsb_batch_lws)
+    void *hdone = nullptr; size_t hdone_cap = 0; // pinned copy of the strip kernel's progress counters
+    bool early_stored = false;             // the last lwsb_batch already copied the results out
     void *pin[2] = {nullptr, nullptr};     // pinned staging for pageable host buffers (lwsb_load / lwsb_store)
     size_t pin_cap = 0;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
@@ -387,6 +395,8 @@ extern "C" int lwsb_destroy(lwsb_ctx *c)
         b->release();
     for (auto &kv : c->twiddles) kv.second.release();
     for (int i = 0; i < 3; ++i) c->raww[i].release();
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->hdone) cudaFreeHost(c->hdone);
     for (int i = 0; i < 2; ++i) {
         if (c->pin[i]) cudaFreeHost(c->pin[i]);
         if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
@@ -619,9 +629,13 @@ extern "C" int lwsb_store(lwsb_ctx *c, void *const *S_out, int where)
     return LWSB_OK;
 }
 
-extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations, int flags)
+// early_out != NULL (one-shot call, page-locked host result buffers): the utterances are listed in groups, and as soon as
+// the last pass of an utterance has written all its frames back (the strips' progress counters, read through a side
+// stream) its rows are copied to early_out[u] by the DMA engine, while the clusters work on the later groups.
+static int batch_impl(lwsb_ctx *c, const double *thresholds, int iterations, int flags, void *const *early_out)
 {
     CHECK_CTX(c);
+    c->early_stored = false;
     if (iterations < 0 || (iterations > 0 && !thresholds)) return fail(c, LWSB_ERR_ARG, "bad thresholds");
     if (int r = check_resident(c)) return r;
     if (iterations == 0) return LWSB_OK; // lws.pyx:219-220
@@ -668,7 +682,9 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
         // work list: one item per (utterance, pass of pl.G sweeps), pass-major, so that the passes of one utterance
         // run on different clusters at the same time, each a few frames behind the previous one
         std::vector<int> items;
-        const int max_pass = build_work_items(nact.data(), c->B, pl.G, items);
+        if (early_out && getenv("LWSB_EARLY_STORE") && atoi(getenv("LWSB_EARLY_STORE")) == 0) early_out = nullptr;
+        const int group = (early_out && c->B >= 32) ? (c->B + 3) / 4 : 0;
+        const int max_pass = build_work_items(nact.data(), c->B, pl.G, items, group);
         const int n_items = (int)(items.size() / 2);
         c->last_work[0] = c->total_bins * iterations; c->last_work[1] = 0; c->last_work[2] = n_items; c->last_work[3] = max_pass;
         for (int b = 0; b < c->B; ++b) c->last_work[1] += (long long)nact[b] * c->T[b] * c->Nreal;
@@ -699,6 +715,45 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
         }
         c->last_kernel = 1; c->last_plan = pl;
         if (int r = end_compute(c)) return r;
+        if (early_out && n_items > 0) {
+            if (!c->copy_stream) CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            if (c->hdone_cap < done_bytes) {
+                if (c->hdone) cudaFreeHost(c->hdone);
+                c->hdone = nullptr; c->hdone_cap = 0;
+                CU(c, cudaHostAlloc(&c->hdone, done_bytes, cudaHostAllocDefault));
+                c->hdone_cap = done_bytes;
+            }
+            CU(c, cudaStreamWaitEvent(c->copy_stream, c->evs[2][0], 0)); // everything before the launch (the load) is complete
+            const unsigned *hd = reinterpret_cast<const unsigned *>(c->hdone);
+            std::vector<char> copied(c->B, 0);
+            int ncopied = 0;
+            const size_t rowb = (size_t)c->Nreal * sizeof(double2);
+            while (ncopied < c->B) {
+                const bool finished = cudaEventQuery(c->ev1) == cudaSuccess;
+                if (!finished) {
+                    CU(c, cudaMemcpyAsync(c->hdone, c->done.p, done_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+                    CU(c, cudaStreamSynchronize(c->copy_stream));
+                }
+                for (int u = 0; u < c->B; ++u) {
+                    if (copied[u]) continue;
+                    bool ready = finished || nact[u] == 0;
+                    if (!ready) {
+                        const int lastp = (nact[u] + pl.G - 1) / pl.G - 1;
+                        ready = true;
+                        for (int k = 0; k < pl.C && ready; ++k)
+                            ready = hd[((size_t)u * max_pass + lastp) * STRIP_MAX_CLUSTER + k] >= (unsigned)c->T[u];
+                    }
+                    if (!ready) continue;
+                    const double2 *src = c->E.as<double2>() + (c->rowbase[u] + c->Q - 1) * (long long)c->P + c->c0;
+                    CU(c, cudaMemcpy2DAsync(early_out[u], rowb, src, (size_t)c->P * sizeof(double2), rowb, c->T[u], cudaMemcpyDeviceToHost,
+                                            c->copy_stream));
+                    copied[u] = 1; ++ncopied;
+                }
+                if (!finished && ncopied < c->B) std::this_thread::sleep_for(std::chrono::microseconds(300));
+            }
+            CU(c, cudaStreamSynchronize(c->copy_stream));
+            c->early_stored = true;
+        }
         unsigned st = 0;
         CU(c, cudaMemcpyAsync(&st, c->status.p, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
@@ -715,6 +770,11 @@ extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations,
     c->launches += 1;
     c->last_kernel = 0;
     return end_compute(c);
+}
+
+extern "C" int lwsb_batch(lwsb_ctx *c, const double *thresholds, int iterations, int flags)
+{
+    return batch_impl(c, thresholds, iterations, flags, nullptr);
 }
 
 extern "C" int lwsb_nofuture(lwsb_ctx *c, int which, const double *thresholds, int iterations, int flags)
@@ -928,7 +988,10 @@ extern "C" int lwsb_batch_lws(lwsb_ctx *c, const void *const *S_in, void *const 
                               int kind, int where, const double *thresholds, int iterations, int flags)
 {
     if (int r = lwsb_load(c, S_in, T, B, Nreal, kind, where)) return r;
-    if (int r = lwsb_batch(c, thresholds, iterations, flags)) return r;
+    bool pinned_out = where == LWSB_HOST && S_out != nullptr;
+    for (int b = 0; b < B && pinned_out; ++b) pinned_out = S_out[b] && !is_pageable(S_out[b]);
+    if (int r = batch_impl(c, thresholds, iterations, flags, pinned_out ? S_out : nullptr)) return r;
+    if (c->early_stored) return LWSB_OK; // the results left while the kernel was running
     return lwsb_store(c, S_out, where);
 }
 

@@ -257,6 +257,30 @@ def test_pageable_buffers_are_staged_in_chunks(gpu):
     assert np.array_equal(Y3, p.batch_lws(np.ascontiguousarray(S[:3]), thresholds=np.zeros(2)))
 
 
+def test_results_leave_while_the_kernel_runs(gpu, oracle):
+    """One-shot batch_lws with page-locked result buffers: the utterances are worked on in groups and every utterance is copied
+    out by the DMA engine as soon as its last pass has written its frames back, while later groups are still in flight.
+    Same bits as with the copy after the kernel (LWSB_EARLY_STORE=0) and as the oracle; ragged batch of 40."""
+    import os
+    po, pg = oracle.lws(512, 128), gpu.lws(512, 128)
+    rng = np.random.default_rng(23)
+    As = [np.abs(po.stft(make_signal("white" if i % 3 else "tonal", 500 + i, int(rng.integers(30000, 60000))))) for i in range(40)]
+    thr = gpu.get_thresholds(24, 3.0, 0.12, 1)   # some utterances drop leading sweeps, pass counts differ
+    Ys = pg.batch_lws(As, thresholds=thr)
+    os.environ["LWSB_EARLY_STORE"] = "0"
+    try:
+        Yl = pg.batch_lws(As, thresholds=thr)
+    finally:
+        del os.environ["LWSB_EARLY_STORE"]
+    for i in range(40):
+        assert np.array_equal(Ys[i], Yl[i]), i
+    for i in (0, 7, 19, 39):
+        _close(Ys[i], po.batch_lws(As[i], thresholds=thr), "early store, utterance %d" % i)
+    big = np.stack([A[:230] for A in As])      # 3-D batch, one pinned block, thresholds nobody exceeds for half the sweeps
+    Y3 = pg.batch_lws(big, thresholds=np.concatenate([np.full(3, 1e9), thr[:6]]))
+    assert np.array_equal(Y3[5], pg.batch_lws(big[5], thresholds=thr[:6]))
+
+
 def test_full_size_properties(gpu):
     """BASELINE.json configs[1] shape (628 x 513, Q = 4, 100 default iterations), 4 utterances:
     size-independent properties instead of an oracle run -- magnitudes preserved, result
