@@ -1027,9 +1027,13 @@ extern "C" int lwsb_run_lws(lwsb_ctx *c, const void *const *S_in, void *const *S
         if (int r = lwsb_online(c, online_thr, online_it, look_ahead, flags)) return r;
         dirty = true;
     }
+    c->early_stored = false;
     if (batch_it > 0) {
         if (dirty) if (int r = restage(c)) return r;
-        if (int r = lwsb_batch(c, batch_thr, batch_it, flags)) return r;
+        bool pinned_out = where == LWSB_HOST && S_out != nullptr;
+        for (int b = 0; b < B && pinned_out; ++b) pinned_out = S_out[b] && !is_pageable(S_out[b]);
+        if (int r = batch_impl(c, batch_thr, batch_it, flags, pinned_out ? S_out : nullptr)) return r;
+        if (c->early_stored) return LWSB_OK;
     }
     return lwsb_store(c, S_out, where);
 }
