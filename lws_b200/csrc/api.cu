@@ -84,19 +84,6 @@ int host_threads()
     return n;
 }
 
-void parallel_memcpy(char *dst, const char *src, size_t bytes)
-{
-    const int nt = bytes < (4u << 20) ? 1 : host_threads();
-    if (nt == 1) { memcpy(dst, src, bytes); return; }
-    std::vector<std::thread> th;
-    const size_t per = (bytes / nt + 4095) & ~(size_t)4095;
-    for (int i = 0; i < nt; ++i) {
-        const size_t lo = std::min(bytes, per * i), hi = std::min(bytes, per * (i + 1));
-        if (hi > lo) th.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
-    }
-    for (auto &t : th) t.join();
-}
-
 bool is_pageable(const void *p)
 {
     cudaPointerAttributes a;
@@ -285,14 +272,31 @@ int staged_copy(lwsb_ctx *c, char *dev, const std::vector<size_t> &offs, const s
             o += n; fill += n;
         }
     const int nc = (int)chunks.size();
-    auto host_side = [&](int k) { // copy chunk k between the caller's arrays and pinned buffer k % 2
+    auto host_side = [&](int k) { // copy chunk k between the caller's arrays and pinned buffer k % 2, the chunk's bytes split over host threads
         char *pb = (char *)c->pin[k % 2];
-        size_t at = 0;
-        for (const Piece &pc : chunks[k]) {
-            if (to_device) parallel_memcpy(pb + at, (const char *)host[pc.b] + pc.off, pc.n);
-            else parallel_memcpy((char *)host[pc.b] + pc.off, pb + at, pc.n);
-            at += pc.n;
+        size_t total = 0;
+        for (const Piece &pc : chunks[k]) total += pc.n;
+        const int nt = total < (4u << 20) ? 1 : host_threads();
+        auto work = [&, pb](size_t lo, size_t hi) { // bytes [lo, hi) of the chunk
+            size_t at = 0;
+            for (const Piece &pc : chunks[k]) {
+                const size_t a = std::max(lo, at), b = std::min(hi, at + pc.n);
+                if (a < b) {
+                    char *hp = (char *)host[pc.b] + pc.off + (a - at);
+                    if (to_device) memcpy(pb + a, hp, b - a);
+                    else memcpy(hp, pb + a, b - a);
+                }
+                at += pc.n;
+            }
+        };
+        if (nt == 1) { work(0, total); return; }
+        std::vector<std::thread> th;
+        const size_t per = ((total + nt - 1) / nt + 4095) & ~(size_t)4095;
+        for (int i = 0; i < nt; ++i) {
+            const size_t lo = std::min(total, per * i), hi = std::min(total, per * (i + 1));
+            if (hi > lo) th.emplace_back(work, lo, hi);
         }
+        for (auto &t : th) t.join();
     };
     auto dma = [&](int k) -> cudaError_t {
         char *pb = (char *)c->pin[k % 2];
