@@ -51,11 +51,21 @@ def istft(spec, fshift, swin, awin=None, fftsize=None, perfectrec=False, *, devi
     fsize = 2 * (N - 1)
     if awin is not None:
         swin = dsp.synthwin(awin, fshift, swin=swin)
-    if fftsize is not None and fftsize != fsize:
-        raise NotImplementedError('istft with fftsize != 2*(Nreal-1) is not supported by the CUDA implementation')
+    if fftsize is None:
+        fftsize = fsize
     swin = np.squeeze(np.asarray(swin, dtype=np.float64))
-    if len(swin) > fsize:
-        raise ValueError('operands could not be broadcast together: frame (%d,) window %s' % (fsize, swin.shape))
+    if swin.ndim == 0:
+        swin = np.full(1, float(swin))
+    if fftsize > len(swin):
+        swin = np.hstack([swin, np.zeros((fftsize - len(swin),))])
+    # lws.pyx:121-126: the frame is the first 2(Nreal-1) samples of an n=fftsize inverse transform, times the (padded)
+    # window.  Unless fftsize == 2(Nreal-1) == len(window) numpy cannot broadcast those; the reference raises
+    # ValueError there (checked against the compiled reference), and so does this.
+    frame_len = min(fsize, fftsize)
+    if len(swin) == 1:
+        swin = np.full(frame_len, swin[0])
+    if frame_len != len(swin) or frame_len != fsize:
+        raise ValueError('operands could not be broadcast together with shapes (%d,) (%d,) ' % (frame_len, len(swin)))
     Sb = np.ascontiguousarray(spec if batched else spec[None], dtype=np.complex128)
     ctx = _ctx(device)
     with ctx.lock:
@@ -78,7 +88,8 @@ def get_consistency(S, fsize, fshift, awin, swin, perfectrec=False, *, device=No
     if S.shape[-1] % 2 != 1:
         raise ValueError('We expect the spectrogram to only have non-negative frequencies')
     if 2 * (S.shape[-1] - 1) != fsize:
-        raise NotImplementedError('get_consistency with fftsize != fsize is not supported by the CUDA implementation')
+        # lws.pyx:143: stft(istft(S)) has fsize/2+1 bins, S has others: numpy's subtraction raises there
+        raise ValueError('operands could not be broadcast together with shapes (%d,) (%d,) ' % (fsize // 2 + 1, S.shape[-1]))
     awin = np.squeeze(np.asarray(awin, dtype=np.float64))
     swin = np.squeeze(np.asarray(swin, dtype=np.float64))
     Sb = np.ascontiguousarray(S if batched else S[None], dtype=np.complex128)

@@ -231,6 +231,13 @@ def test_api_behaviours(gpu):
     assert Y32.dtype == np.complex128
     xx = np.random.default_rng(4).standard_normal(1000)
     assert np.abs(p.istft(p.stft(xx))[:1000] - xx).max() < 1e-13
+    # a synthesis window shorter than the frame is zero-padded up to fftsize (lws.pyx:111-112)
+    import lws_b200 as mod
+    Xs = p.stft(xx)
+    fs = 2 * (Xs.shape[1] - 1)
+    a = mod.istft(Xs, p.fshift, p.swin[: fs // 2])
+    b = mod.istft(Xs, p.fshift, np.hstack([p.swin[: fs // 2], np.zeros(fs - fs // 2)]), fftsize=fs)
+    assert np.array_equal(a, b) and np.abs(a).max() > 0
     assert p.get_consistency(p.stft(xx)) > 250.0
     assert gpu.lws(512, 100).W.shape == (512, 6, 6)  # per-frequency weights: the *fractionalQ path (test_fractional_*)
 

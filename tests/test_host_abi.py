@@ -103,6 +103,14 @@ def test_api_checks_before_any_kernel():
         lws_b200.lws(32, 8, fftsize=35)
     with pytest.raises(TypeError):
         lws_b200.lws(np.ones((2, 32)), 8)
+    # module-level istft / get_consistency with an fftsize that is not 2(Nreal-1): the reference's numpy expressions cannot
+    # broadcast (lws.pyx:121-126, 143) and raise ValueError; checked against the compiled reference for these shapes
+    S17 = np.ones((6, 33), dtype=np.complex128)
+    for fft, wlen in ((32, 64), (128, 64), (128, 128), (66, 64), (64, 128)):
+        with pytest.raises(ValueError, match="broadcast"):
+            lws_b200.istft(S17, 16, np.ones(wlen), fftsize=fft)
+    with pytest.raises(ValueError, match="broadcast"):
+        lws_b200.get_consistency(S17, 128, 16, np.ones(128), np.ones(128))
     assert np.array_equal(lws_b200.get_thresholds(4, 100, 0.1, 1), 100 * np.exp(-0.1 * np.arange(4)))
 
 
