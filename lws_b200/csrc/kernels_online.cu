@@ -524,6 +524,231 @@ k_online_duo(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *thr
             for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
 }
 
+// ---------------------------------------------------------------- one bin per step, K warps per task taking turns (Q <= 4)
+// The chain of a bin (centre-frame terms that see the bin committed just before, the ordered sum, sqrt, two divisions) is a
+// dependent sequence no schedule can shorten; the term values of the other frames are not on it.  k_online_duo still runs
+// them one after the other in every lane.  Here a task (row update) is served by K lanes, lane l of K different warps
+// ("roles"): role rho takes the bins of bin-steps b = rho, rho + K, ...  While role rho runs the chain of bin-step b, roles
+// rho + 1 .. rho + K - 1 are forming the term values of bin-steps b + 1 .. b + K - 1, so that per bin-step only a chain is on
+// the critical path.  Hand-over is a named barrier per bin-step: the warps that committed bin-step b and the warps about to run
+// the chain of b + 1 meet on barrier 1 + b mod K (all groups of 32 tasks: consecutive tasks sit in neighbouring lanes and
+// groups).
+//
+// Dependencies (bin time b: task j is on bin b - S j).  The term values of task j, bin c read columns c - L .. c + L of other
+// rows; task j - 1 must have committed through column c + L and task j + 1 must not have reached column c - L.  A role starts
+// the values of bin-step b after its own hand-over of bin-step b - K, when all bin-steps <= b - K are complete: task j - 1 is
+// then through column c - K + S >= c + L iff S >= K + L; the chains of bin-steps > b cannot start before b's, so task j + 1
+// is at most on column c + K - 1 - S < c - L.  Centre-frame terms k < K read bins committed less than K bin-steps ago: they
+// are formed after the hand-over, k >= K before (not within 2L bins of the ends of the spectrum, where a neighbour can be the
+// mirror cell of a bin committed less than K bin-steps ago).
+//
+// Everything that depends on the residue of the bin, on the kind of row update or on the parity rule of the Q4 folding is
+// per-lane DATA (weight rows, row offsets with the all-zero row standing in for frames that are not used, a sign mask), not
+// code: one body for every bin, S need not be a multiple of Q.  A term the reference skips (|W| <= 1e-12, no centre frame)
+// gets the value -0.0: the running sum starts at +0.0 and can never be -0.0, so adding a zero of either sign leaves its bits.
+template <int K>
+__device__ __forceinline__ void flow_bar(long long b, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(b % K)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ double flow_flip(double x, unsigned m) { return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x)); }
+__device__ __forceinline__ double flow_keep(double x, bool keep) { return keep ? x : -0.0; }
+
+template <int Q, int FOLD, int K>
+__global__ void __launch_bounds__(256)
+k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *thresholds, int iters, int LA, int R, int pitch,
+              int S, unsigned *status)
+{
+    static_assert(Q <= 4 && Q >= 2, "frame pairs held in registers");
+    constexpr int L = OL, NP = Q - 1, PER_R = OnlineVals<Q, FOLD>::PER_R;
+    extern __shared__ __align__(16) unsigned char online_smem[];
+    double2 *ring = reinterpret_cast<double2 *>(online_smem);
+    double2 *zrow = ring + (size_t)R * pitch;                       // a row of zeros: the frames m + r a row update does not use
+    double2 *w2 = zrow + pitch;                                     // (wr, wi)[3][Q][Q][L + 1]
+    unsigned *wf = reinterpret_cast<unsigned *>(w2 + 3 * Q * Q * (L + 1)); // flags [3][Q][Q]
+    for (int i = threadIdx.x; i < 3 * Q * Q * (L + 1); i += blockDim.x)
+        w2[i] = make_double2((&w.wr[0][0][0][0])[i], (&w.wi[0][0][0][0])[i]);
+    for (int i = threadIdx.x; i < 3 * Q * Q; i += blockDim.x) wf[i] = (&w.flag[0][0][0])[i];
+    for (int i = threadIdx.x; i < pitch; i += blockDim.x) zrow[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    const int u = blockIdx.x;
+    const int T = v.T[u], Nreal = v.Nreal, P = v.P;
+    const int Np = Nreal + 2 * L, Tp = T + 2 * (Q - 1), rmask = R - 1;
+    double2 *E0 = v.E + v.rowbase[u] * (long long)P + (v.c0 - L); // extended (row 0, column 0)
+    const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
+    const double mean = v.mean_amp[u];
+    const long long n = lwsb_online_chain_len(T, iters, LA);
+    const long long bend = (long long)S * (n - 1) + (Nreal - 1) + 1; // one empty bin-step closes the last hand-over
+    const int nall = blockDim.x, G = nall / (32 * K), nt = 32 * G;   // nt tasks in flight, K lanes each
+    const int wid = threadIdx.x >> 5, role = wid / G, tix = (wid % G) * 32 + (threadIdx.x & 31);
+    const int handover = 2 * nt;                                     // threads on a hand-over barrier
+    int lo = 0, hi = -1;                                             // extended rows [lo, hi] are resident
+    long long jc = -1, jhi_prev = 0;
+    int d = (nt - tix) % nt;                                         // (jhi - tix) mod nt at jhi = 0
+    // per-lane constants of the task (and of the residue of this role's bins)
+    int off_m[NP], off_p[NP], off_own = 0, wofs[NP], wofs_n[NP], wofs_c = 0, cframe = 0, row = Q - 1;
+    unsigned flg[NP], flg_n[NP], flg_c = 0, sgn[NP];
+#pragma unroll
+    for (int s = 0; s < NP; ++s) { off_m[s] = off_p[s] = wofs[s] = wofs_n[s] = 0; flg[s] = flg_n[s] = sgn[s] = 0; }
+    int pc = -1;
+    double thr = 0.0, a_next = 0.0;
+    for (long long b = role; b <= bend; b += K) {
+        bool waited = false;
+        {   // residency: the front of the chain reaches a new row update at multiples of S; each role meets each multiple once
+            const long long bs = b / S * S;
+            if (bs > b - K) {
+                const long long jh = min(bs / S, n - 1);
+                long long jlo = bs < Nreal ? 0 : (bs - (Nreal - 1) + S - 1) / S;
+                if (jlo > n - 1) jlo = n - 1;
+                const int need_hi = min(Tp - 1, lwsb_online_frame(iters, LA, jh) + 2 * (Q - 1));
+                const int need_lo = max(0, lwsb_online_frame(iters, LA, jlo) - LA);
+                if (need_hi > hi) {
+                    // drain: the role of bin-step bs takes its hand-over first (the committers of bs - 1 wait for it), then
+                    // everybody meets: all bin-steps < bs are complete and none >= bs has begun
+                    if (b == bs && b > 0) { flow_bar<K>(b - 1, handover); waited = true; }
+                    __syncthreads();
+                    if (need_hi - need_lo + 1 > R && threadIdx.x == 0) atomicCAS(status, 0u, 0xE1000000u | (unsigned)u);
+                    for (int e = lo; e < need_lo; ++e) // rows the chain has left: back to global memory
+                        if (e >= Q - 1 && e < T + Q - 1)
+                            for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+                    __syncthreads();
+                    for (int e = hi + 1; e <= need_hi; ++e) // rows the chain is about to reach
+                        for (int x = threadIdx.x; x < Np; x += nall) ring[(size_t)(e & rmask) * pitch + x] = E0[(long long)e * P + x];
+                    __syncthreads();
+                }
+                if (need_hi > hi) { lo = need_lo; hi = need_hi; }
+            }
+        }
+        // the row update this lane works on: j = jhi - d, d = (jhi - tix) mod nt kept incrementally (K <= S: jhi grows by <= 1)
+        const long long jhi = b / S;
+        d += (int)(jhi - jhi_prev); if (d >= nt) d -= nt;
+        jhi_prev = jhi;
+        const long long j = jhi - d;
+        bool act = false;
+        int c = 0;
+        double a = 0.0;
+        if (j >= 0 && j < n) {
+            c = (int)(b - (long long)S * j);
+            if (c < Nreal) {
+                const int p = c % Q;
+                if (j != jc || p != pc) {
+                    LwsbOnlineTask task = lwsb_online_decode(T, iters, LA, Q, j);
+                    if (j != jc) {
+                        thr = task.thr < 0 ? 0.0 : __dmul_rn(thresholds[task.thr], mean); // lws.pyx:361, lwslib.cpp:1467
+                        a = __ldg(A0 + (long long)task.row * P + L + c);
+                    } else a = a_next;
+                    jc = j; pc = p;
+                    row = task.row; cframe = task.cframe;
+                    const int pn = (Q - p) % Q;
+                    const bool odd = FOLD == LWSB_FOLD_Q4 && (p & 1);
+                    off_own = (row & rmask) * pitch;
+                    wofs_c = ((task.which * Q + p) * Q + 0) * (L + 1);
+                    flg_c = cframe ? wf[(task.which * Q + p) * Q + 0] : 0u;
+#pragma unroll
+                    for (int s = 0; s < NP; ++s) {
+                        // the frame pairs in the order the reference adds them: odd bins of the Q4 folding take r = 1, 3
+                        // (sign-flipped) then 2 (lwslib.cpp:953-1052)
+                        const int r = odd ? (s == 0 ? 1 : (s == 1 ? 3 : 2)) : s + 1;
+                        sgn[s] = (odd && s < 2) ? 0x80000000u : 0u;
+                        off_m[s] = ((row - r) & rmask) * pitch;
+                        off_p[s] = r < task.rframe ? ((row + r) & rmask) * pitch : R * pitch; // R * pitch: the zero row
+                        wofs[s] = ((task.which * Q + p) * Q + r) * (L + 1);
+                        wofs_n[s] = ((task.which * Q + pn) * Q + r) * (L + 1);
+                        flg[s] = wf[(task.which * Q + p) * Q + r];
+                        flg_n[s] = wf[(task.which * Q + pn) * Q + r];
+                    }
+                } else a = a_next;
+                if (c + K < Nreal) a_next = __ldg(A0 + (long long)row * P + L + c + K); // this lane's next bin
+                act = a > thr; // lwslib.cpp:295-296
+            }
+        }
+        // ---- term values of the other frames, centre-frame values k >= K
+        const int col = L + c;
+        const bool edge = c <= 2 * L || c >= Nreal - 1 - 2 * L;
+        OnlineVals<Q, FOLD> vals;
+        double cvr[L], cvi[L];
+        double2 wc[K < L ? K : L]; // centre weights k < K, fetched before the hand-over
+        const double2 *own = ring + off_own + col;
+        if (act) {
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+                const double2 *pm = ring + off_m[s] + col, *pp = ring + off_p[s] + col, *ws = w2 + wofs[s];
+                const int base = s * PER_R;
+                {
+                    const double2 bb = pm[0], cc = pp[0], ww = ws[0];
+                    double vr, vi;
+                    online_value(ww.x, ww.y, bb.x, bb.y, cc.x, cc.y, vr, vi);
+                    vals.r[base] = flow_keep(vr, flg[s] & 1u); vals.i[base] = flow_keep(vi, flg[s] & 1u);
+                }
+#pragma unroll
+                for (int k = 1; k <= L; ++k) {
+                    const double2 e1 = pm[-k], e4 = pm[k], e2 = pp[k], e3 = pp[-k], ww = ws[k];
+                    const bool keep = (flg[s] >> k) & 1u;
+                    if (FOLD == LWSB_FOLD_ANY) {
+                        const double2 wn = (w2 + wofs_n[s])[k];
+                        const bool keepn = (flg_n[s] >> k) & 1u;
+                        double vr, vi;
+                        online_value(ww.x, ww.y, e1.x, e1.y, e3.x, e3.y, vr, vi);
+                        vals.r[base + 2 * k - 1] = flow_keep(vr, keep); vals.i[base + 2 * k - 1] = flow_keep(vi, keep);
+                        online_value(wn.x, wn.y, e2.x, e2.y, e4.x, e4.y, vr, vi);
+                        vals.r[base + 2 * k] = flow_keep(vr, keepn); vals.i[base + 2 * k] = flow_keep(vi, keepn);
+                    } else {
+                        // b = e1 -+ e2, c = e3 -+ e4 (lwslib.cpp:204-207, 228-231): x - y == x + (-y) bit for bit
+                        const double br = __dadd_rn(e1.x, flow_flip(e2.x, sgn[s])), bi = __dadd_rn(e1.y, flow_flip(e2.y, sgn[s]));
+                        const double cr = __dadd_rn(e3.x, flow_flip(e4.x, sgn[s])), ci = __dadd_rn(e3.y, flow_flip(e4.y, sgn[s]));
+                        double vr, vi;
+                        online_value(ww.x, ww.y, br, bi, cr, ci, vr, vi);
+                        vals.r[base + k] = flow_keep(vr, keep); vals.i[base + k] = flow_keep(vi, keep);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 1; k <= L; ++k) {
+                if (k < K) wc[k - 1] = (w2 + wofs_c)[k];
+                else if (!edge) {
+                    const double2 bb = own[-k], cc = own[k], ww = (w2 + wofs_c)[k];
+                    double vr, vi;
+                    online_value(ww.x, ww.y, bb.x, bb.y, cc.x, cc.y, vr, vi);
+                    cvr[k - 1] = flow_keep(vr, (flg_c >> k) & 1u); cvi[k - 1] = flow_keep(vi, (flg_c >> k) & 1u);
+                }
+            }
+        }
+        __syncwarp();
+        if (b > 0 && !waited) flow_bar<K>(b - 1, handover); // every bin of bin-step b - 1 is committed
+        // ---- the chain: centre-frame values k < K, the sum in the reference's order, projection, commit
+        if (act) {
+#pragma unroll
+            for (int k = 1; k <= L; ++k)
+                if (k < K || edge) {
+                    const double2 bb = own[-k], cc = own[k];
+                    const double2 ww = k < K ? wc[k - 1] : (w2 + wofs_c)[k];
+                    double vr, vi;
+                    online_value(ww.x, ww.y, bb.x, bb.y, cc.x, cc.y, vr, vi);
+                    cvr[k - 1] = flow_keep(vr, (flg_c >> k) & 1u); cvi[k - 1] = flow_keep(vi, (flg_c >> k) & 1u);
+                }
+            double tr = 0.0, ti = 0.0;
+#pragma unroll
+            for (int k = 0; k < L; ++k) { tr = __dadd_rn(tr, cvr[k]); ti = __dadd_rn(ti, cvi[k]); }
+#pragma unroll
+            for (int i = 0; i < OnlineVals<Q, FOLD>::N; ++i) { tr = __dadd_rn(tr, vals.r[i]); ti = __dadd_rn(ti, vals.i[i]); }
+            double2 val;
+            if (x_project(tr, ti, a, val)) {
+                double2 *Rrow = ring + off_own;
+                Rrow[L + c] = val;
+                if (c >= 1 && c <= L) Rrow[L - c] = make_double2(val.x, -val.y);
+                else if (c >= Nreal - 1 - L && c <= Nreal - 2) Rrow[L + 2 * (Nreal - 1) - c] = make_double2(val.x, -val.y);
+            }
+        }
+        __syncwarp();
+        if (b < bend) flow_bar<K>(b, handover);
+    }
+    __syncthreads();
+    for (int e = lo; e <= hi; ++e)
+        if (e >= Q - 1 && e < T + Q - 1)
+            for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+}
+
 template <int Q, int FOLD, int P>
 __device__ __forceinline__ void online_sum_for_residue(int p, const OnlineRingCell &E, const OnlineW<Q> &w, int ws, int rframe,
                                                        int cframe, double &tr, double &ti)
@@ -636,10 +861,20 @@ int online_max_span(int T, int Nreal, int S, int Q, int iters, int LA)
 
 template <int Q, int FOLD>
 cudaError_t launch_t(const LwsbView &v, const OnlineW<Q> &w, const double *thr, int iters, int LA, int R, int pitch, int S, int nt,
-                     size_t bytes, size_t smem_limit, unsigned *status, int *which_kernel, cudaStream_t s)
+                     size_t bytes, size_t smem_limit, unsigned *status, int *which_kernel, int flowK, cudaStream_t s)
 {
     *which_kernel = 1;
     if constexpr (Q <= 4) {
+        if (flowK > 0) { // K warps per task taking turns; `nt` is the CTA size, `bytes` includes the zero row and the weights
+            auto kern4 = flowK == 4 ? k_online_flow<Q, FOLD, 4> : (flowK == 3 ? k_online_flow<Q, FOLD, 3> : k_online_flow<Q, FOLD, 2>);
+            if (bytes > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                if (e != cudaSuccess) return e;
+            }
+            kern4<<<v.B, nt, bytes, s>>>(v, w, thr, iters, LA, R, pitch, S, status);
+            *which_kernel = 4;
+            return cudaGetLastError();
+        }
         const char *e_duo = getenv("LWSB_ONLINE_DUO");
         if (S >= 2 + OL && S % 2 == 0 && 2 * nt <= 256 && !(e_duo && atoi(e_duo) == 0)) { // two bins per step on two lanes
             auto kern3 = k_online_duo<Q, FOLD>;
@@ -673,7 +908,8 @@ cudaError_t launch_t(const LwsbView &v, const OnlineW<Q> &w, const double *thr, 
 
 template <int Q>
 cudaError_t launch_q(const LwsbView &v, const double *const *wr, const double *const *wi, int fold, const double *thr, int iters,
-                     int LA, int R, int pitch, int S, int nt, size_t bytes, size_t smem_limit, unsigned *status, int *which_kernel, cudaStream_t s)
+                     int LA, int R, int pitch, int S, int nt, size_t bytes, size_t smem_limit, unsigned *status, int *which_kernel, int flowK,
+                     cudaStream_t s)
 {
     OnlineW<Q> w;
     for (int ws = 0; ws < 3; ++ws)
@@ -687,9 +923,9 @@ cudaError_t launch_q(const LwsbView &v, const double *const *wr, const double *c
                 }
                 w.flag[ws][p][r] = f;
             }
-    if (fold == LWSB_FOLD_ANY) return launch_t<Q, LWSB_FOLD_ANY>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s);
-    if constexpr (Q == 4) { if (fold == LWSB_FOLD_Q4) return launch_t<4, LWSB_FOLD_Q4>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); }
-    if constexpr (Q == 2) { if (fold == LWSB_FOLD_Q2) return launch_t<2, LWSB_FOLD_Q2>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); }
+    if (fold == LWSB_FOLD_ANY) return launch_t<Q, LWSB_FOLD_ANY>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, flowK, s);
+    if constexpr (Q == 4) { if (fold == LWSB_FOLD_Q4) return launch_t<4, LWSB_FOLD_Q4>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, flowK, s); }
+    if constexpr (Q == 2) { if (fold == LWSB_FOLD_Q2) return launch_t<2, LWSB_FOLD_Q2>(v, w, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, flowK, s); }
     return cudaErrorInvalidValue;
 }
 
@@ -706,7 +942,35 @@ bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const d
     if (v.L != OL || !(Q == 2 || Q == 4 || Q == 8)) return false;
     // smallest multiple of Q >= L + 1 (Q > 4: one bin per step) or >= L + 2 (Q <= 4: two bins per step): every thread of a
     // step on the same residue, and the bins a task takes in one step stay clear of its neighbours' in the chain
-    const int S = Q <= 4 ? (OL + 2 + Q - 1) / Q * Q : (OL + 1 + Q - 1) / Q * Q;
+    int S = Q <= 4 ? (OL + 2 + Q - 1) / Q * Q : (OL + 1 + Q - 1) / Q * Q;
+    int flowK = 0;
+    if (Q <= 4) { // k_online_flow: K warps per task, any lag S >= K + L (LWSB_ONLINE_FLOW=0 disables, =2/3 sets K; LWSB_ONLINE_FLOW_S the lag)
+        const char *e_flow = getenv("LWSB_ONLINE_FLOW"), *e_s = getenv("LWSB_ONLINE_FLOW_S");
+        int K = e_flow ? atoi(e_flow) : 4;
+        if (K == 1 || K > 4) K = 4;
+        if (K >= 2) {
+            const int Sf = std::max(K + OL, e_s ? atoi(e_s) : 0);
+            const int tasks = (v.Nreal + Sf - 1) / Sf + 1, G = (tasks + 31) / 32;
+            if (G * K * 32 <= 256) {
+                int spanf = 0, lastTf = -1;
+                for (int b = 0; b < v.B; ++b)
+                    if (T_host[b] != lastTf) { lastTf = T_host[b]; spanf = std::max(spanf, online_max_span(lastTf, v.Nreal, Sf, Q, iters, LA)); }
+                int Rf = 8;
+                while (Rf < spanf) Rf *= 2;
+                int pitchf = v.Nreal + 2 * OL;
+                if ((pitchf & 1) == 0) ++pitchf;
+                const size_t bytesf = (size_t)(Rf + 1) * pitchf * sizeof(double2) + (size_t)3 * Q * Q * ((OL + 1) * 16 + 4);
+                if (bytesf + 1024 <= smem_limit) {
+                    flowK = K; S = Sf;
+                    switch (Q) {
+                    case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, Rf, pitchf, S, G * K * 32, bytesf, smem_limit, status, which_kernel, flowK, s); break;
+                    case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, Rf, pitchf, S, G * K * 32, bytesf, smem_limit, status, which_kernel, flowK, s); break;
+                    }
+                    return true;
+                }
+            }
+        }
+    }
     int span = 0, lastT = -1;
     for (int b = 0; b < v.B; ++b) // exact span for every distinct length of the batch
         if (T_host[b] != lastT) { lastT = T_host[b]; span = std::max(span, online_max_span(lastT, v.Nreal, S, Q, iters, LA)); }
@@ -720,9 +984,9 @@ bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const d
     nt = (nt + 31) / 32 * 32;
     if (nt > 256) return false;
     switch (Q) {
-    case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); break;
-    case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); break;
-    case 8: *err = launch_q<8>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, s); break;
+    case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, flowK, s); break;
+    case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, flowK, s); break;
+    case 8: *err = launch_q<8>(v, wr_host, wi_host, fold, thr, iters, LA, R, pitch, S, nt, bytes, smem_limit, status, which_kernel, flowK, s); break;
     }
     return true;
 }

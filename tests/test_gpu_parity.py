@@ -320,7 +320,7 @@ def test_cfg3_cfg4_one_utterance_vs_oracle(gpu, oracle):
     _close(pg.nofuture_lws(A), po.nofuture_lws(A), "cfg3 nofuture")
     _close(pg.online_lws(A), po.online_lws(A), "cfg3 online")
     from lws_b200 import api
-    assert api._context(0).last_online_kernel() == 3
+    assert api._context(0).last_online_kernel() == 4
     _close(pg.run_lws(A), po.run_lws(A), "cfg4 run_lws")
     # a batch of three: every member equals the single-utterance result
     Ys = pg.online_lws(np.stack([A, A[::-1], A]))
@@ -330,7 +330,7 @@ def test_cfg3_cfg4_one_utterance_vs_oracle(gpu, oracle):
 @pytest.mark.parametrize("fs,hop,la,its,n", [(1024, 256, 3, 10, 40000), (512, 128, 3, 4, 9000), (512, 128, 5, 3, 9000), (512, 128, 1, 5, 5000),
                                              (512, 128, 0, 6, 5000), (64, 16, 3, 10, 4000), (128, 64, 1, 7, 6000), (2048, 256, 3, 3, 30000)])
 def test_online_ring_kernels(gpu, oracle, fs, hop, la, its, n):
-    """The shared-memory ring kernel of online_lws (two bins per step on two lanes) and the generic fallback against the
+    """The shared-memory ring kernel of online_lws (K warps per task taking turns) and the generic fallback against the
     oracle over look-aheads, iteration counts and ragged batches."""
     from lws_b200 import api
     ctx = api._context(0)
@@ -339,12 +339,38 @@ def test_online_ring_kernels(gpu, oracle, fs, hop, la, its, n):
     As = [np.abs(po.stft(make_signal(k, 31 + i, n + 700 * i))) for i, k in enumerate(("tonal", "white", "tonal"))]
     for thr in (None, np.zeros(its)):
         Ys = pg.online_lws(As, thresholds=thr)
-        want = 0 if fs // hop > 4 else 3  # Q = 8 at 1025 bins: ring too large for shared memory, generic kernel
+        want = 0 if fs // hop > 4 else 4  # Q = 8 at 1025 bins: ring too large for shared memory, generic kernel
         assert ctx.last_online_kernel() == want, ctx.last_online_kernel()
         for A, Y in zip(As, Ys):
             _close(Y, po.online_lws(A, thresholds=thr), "online ring kernel, LA=%d" % la)
     for T in (1, 2, 3, 5):  # fewer frames than look-ahead + 1, a single frame
         _close(pg.online_lws(As[0][:T]), po.online_lws(As[0][:T]), "online T=%d" % T)
+
+
+@pytest.mark.parametrize("flow,lag,want", [("0", None, 3), ("2", None, 4), ("3", None, 4), ("4", "10", 4), ("4", "13", 4)])
+@pytest.mark.parametrize("fs,hop,la,its", [(512, 128, 3, 4), (128, 64, 2, 5)])
+def test_online_kernel_choices(gpu, oracle, monkeypatch, flow, lag, want, fs, hop, la, its):
+    """The other shapes of the online chain kernel -- two lanes per task (LWSB_ONLINE_FLOW=0), 2 or 3 warps per task, longer
+    lags between row updates -- give the same bits."""
+    from lws_b200 import api
+    monkeypatch.setenv("LWSB_ONLINE_FLOW", flow)
+    if lag:
+        monkeypatch.setenv("LWSB_ONLINE_FLOW_S", lag)
+    kw = dict(look_ahead=la, online_iterations=its)
+    po, pg = oracle.lws(fs, hop, **kw), gpu.lws(fs, hop, **kw)
+    As = [np.abs(po.stft(make_signal(k, 77 + i, 7000 + 900 * i))) for i, k in enumerate(("white", "tonal"))]
+    for thr in (None, np.zeros(its)):
+        Ys = pg.online_lws(As, thresholds=thr)
+        assert api._context(0).last_online_kernel() == want
+        for A, Y in zip(As, Ys):
+            _close(Y, po.online_lws(A, thresholds=thr), "online kernel flow=%s lag=%s" % (flow, lag))
+    # the anyQ formulas on the same kernel (LWSB_FORCE_ANYQ) against the oracle made to take its anyQ branch
+    from lws_b200 import _native
+    thr = np.ones(its)
+    Yg = gpu.online_lws(As[0], pg.W, pg.W_ai, pg.W_af, thr, la, hop, flags=_native.FORCE_ANYQ)
+    assert api._context(0).last_online_kernel() == want
+    monkeypatch.setattr(oracle, "_fold", lambda Q, Qprime, simp, Nreal: 0)
+    _close(Yg, oracle.online_lws(As[0], po.W, po.W_ai, po.W_af, thr, la, hop), "online anyQ formulas, flow=%s" % flow)
 
 
 @pytest.mark.parametrize("fs,hop,kw,chunks", [(512, 128, {}, (1, 2, 3, 5, 8, 13, 40)), (64, 16, {"look_ahead": 0}, (7,)), (64, 8, {"look_ahead": 2}, (1, 30)),
