@@ -538,22 +538,35 @@ k_online_duo(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *thr
 // rows; task j - 1 must have committed through column c + L and task j + 1 must not have reached column c - L.  A role starts
 // the values of bin-step b after its own hand-over of bin-step b - K, when all bin-steps <= b - K are complete: task j - 1 is
 // then through column c - K + S >= c + L iff S >= K + L; the chains of bin-steps > b cannot start before b's, so task j + 1
-// is at most on column c + K - 1 - S < c - L.  Centre-frame terms k < K read bins committed less than K bin-steps ago: they
-// are formed after the hand-over, k >= K before (not within 2L bins of the ends of the spectrum, where a neighbour can be the
-// mirror cell of a bin committed less than K bin-steps ago).
+// is at most on column c + K - 1 - S < c - L.  The centre-frame terms read bins (and mirror cells) of the task's own row
+// committed up to one bin-step ago: all of them are formed after the hand-over; only k = 1 is on the critical path, the
+// others fill the bubbles of the dependent sum.
 //
 // Everything that depends on the residue of the bin, on the kind of row update or on the parity rule of the Q4 folding is
 // per-lane DATA (weight rows, row offsets with the all-zero row standing in for frames that are not used, a sign mask), not
 // code: one body for every bin, S need not be a multiple of Q.  A term the reference skips (|W| <= 1e-12, no centre frame)
 // gets the value -0.0: the running sum starts at +0.0 and can never be -0.0, so adding a zero of either sign leaves its bits.
-template <int K>
-__device__ __forceinline__ void flow_bar(long long b, int count)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(b % K)), "r"(count) : "memory");
-}
-
+// Shared memory is addressed with 32-bit shared-window addresses and immediate offsets (ld.shared / st.shared).
+__device__ __forceinline__ void flow_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ double flow_flip(double x, unsigned m) { return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x)); }
 __device__ __forceinline__ double flow_keep(double x, bool keep) { return keep ? x : -0.0; }
+
+template <int OFF> // cell at byte address a + 16 OFF of the shared window
+__device__ __forceinline__ double2 flow_ld(unsigned a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(16 * OFF) : "memory");
+    return v;
+}
+__device__ __forceinline__ void flow_st(unsigned a, double x, double y)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+template <int I, int N, class F>
+__device__ __forceinline__ void flow_for(F &&f)
+{
+    if constexpr (I < N) { f(std::integral_constant<int, I>{}); flow_for<I + 1, N>(f); }
+}
 
 template <int Q, int FOLD, int K>
 __global__ void __launch_bounds__(256)
@@ -565,13 +578,17 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
     extern __shared__ __align__(16) unsigned char online_smem[];
     double2 *ring = reinterpret_cast<double2 *>(online_smem);
     double2 *zrow = ring + (size_t)R * pitch;                       // a row of zeros: the frames m + r a row update does not use
-    double2 *w2 = zrow + pitch;                                     // (wr, wi)[3][Q][Q][L + 1]
-    unsigned *wf = reinterpret_cast<unsigned *>(w2 + 3 * Q * Q * (L + 1)); // flags [3][Q][Q]
+    // (wr, wi)[3][Q] blocks of Q (L + 1) cells + 1 of padding: the lanes of a warp differ in weight set and residue, the odd
+    // block stride spreads them over the bank groups (without it all of them collide on one: 3 Q-way conflicts per load)
+    constexpr int WB = Q * (L + 1) + 1;
+    double2 *w2 = zrow + pitch;
+    unsigned *wf = reinterpret_cast<unsigned *>(w2 + 3 * Q * WB); // flags [3][Q][Q]
     for (int i = threadIdx.x; i < 3 * Q * Q * (L + 1); i += blockDim.x)
-        w2[i] = make_double2((&w.wr[0][0][0][0])[i], (&w.wi[0][0][0][0])[i]);
+        w2[i / (Q * (L + 1)) * WB + i % (Q * (L + 1))] = make_double2((&w.wr[0][0][0][0])[i], (&w.wi[0][0][0][0])[i]);
     for (int i = threadIdx.x; i < 3 * Q * Q; i += blockDim.x) wf[i] = (&w.flag[0][0][0])[i];
     for (int i = threadIdx.x; i < pitch; i += blockDim.x) zrow[i] = make_double2(0.0, 0.0);
     __syncthreads();
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring), w2_s = (unsigned)__cvta_generic_to_shared(w2);
     const int u = blockIdx.x;
     const int T = v.T[u], Nreal = v.Nreal, P = v.P;
     const int Np = Nreal + 2 * L, Tp = T + 2 * (Q - 1), rmask = R - 1;
@@ -579,114 +596,112 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
     const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
     const double mean = v.mean_amp[u];
     const long long n = lwsb_online_chain_len(T, iters, LA);
-    const long long bend = (long long)S * (n - 1) + (Nreal - 1) + 1; // one empty bin-step closes the last hand-over
+    long long bend = (long long)S * (n - 1) + (Nreal - 1) + 1; // one empty bin-step closes the last hand-over
     const int nall = blockDim.x, G = nall / (32 * K), nt = 32 * G;   // nt tasks in flight, K lanes each
     const int wid = threadIdx.x >> 5, role = wid / G, tix = (wid % G) * 32 + (threadIdx.x & 31);
-    const int handover = 2 * nt;                                     // threads on a hand-over barrier
+    int handover = 2 * nt;                                           // threads on a hand-over barrier
+    int bar_mine = 1 + role, bar_prev = 1 + (role + K - 1) % K;      // b mod K == role for every bin-step of this warp
+    // loop invariants that sit between a commit and its hand-over: kept in registers (opaque to rematerialisation)
+    asm volatile("" : "+r"(handover), "+r"(bar_mine), "+r"(bar_prev), "+l"(bend));
     int lo = 0, hi = -1;                                             // extended rows [lo, hi] are resident
-    long long jc = -1, jhi_prev = 0;
+    long long jc = -1, jhi = 0;
+    int bmod = role;                                                 // b mod S (role < K <= S)
     int d = (nt - tix) % nt;                                         // (jhi - tix) mod nt at jhi = 0
-    // per-lane constants of the task (and of the residue of this role's bins)
-    int off_m[NP], off_p[NP], off_own = 0, wofs[NP], wofs_n[NP], wofs_c = 0, cframe = 0, row = Q - 1;
+    // per-lane constants of the task (and of the residue of this role's bins): byte offsets into the ring / weight tables
+    unsigned off_m[NP], off_p[NP], off_own = 0, wofs[NP], wofs_n[NP], wofs_c = 0;
     unsigned flg[NP], flg_n[NP], flg_c = 0, sgn[NP];
+    int row = Q - 1;
 #pragma unroll
     for (int s = 0; s < NP; ++s) { off_m[s] = off_p[s] = wofs[s] = wofs_n[s] = 0; flg[s] = flg_n[s] = sgn[s] = 0; }
     int pc = -1;
     double thr = 0.0, a_next = 0.0;
     for (long long b = role; b <= bend; b += K) {
         bool waited = false;
-        {   // residency: the front of the chain reaches a new row update at multiples of S; each role meets each multiple once
-            const long long bs = b / S * S;
-            if (bs > b - K) {
-                const long long jh = min(bs / S, n - 1);
-                long long jlo = bs < Nreal ? 0 : (bs - (Nreal - 1) + S - 1) / S;
-                if (jlo > n - 1) jlo = n - 1;
-                const int need_hi = min(Tp - 1, lwsb_online_frame(iters, LA, jh) + 2 * (Q - 1));
+        if (bmod < K) { // a multiple of S in (b - K, b]: the front of the chain reaches a new row update (each role sees each once)
+            const long long bs = b - bmod;
+            const long long jh = min(jhi, n - 1);
+            long long jlo = bs < Nreal ? 0 : (bs - (Nreal - 1) + S - 1) / S;
+            if (jlo > n - 1) jlo = n - 1;
+            const int need_hi = min(Tp - 1, lwsb_online_frame(iters, LA, jh) + 2 * (Q - 1));
+            if (need_hi > hi) {
                 const int need_lo = max(0, lwsb_online_frame(iters, LA, jlo) - LA);
-                if (need_hi > hi) {
-                    // drain: the role of bin-step bs takes its hand-over first (the committers of bs - 1 wait for it), then
-                    // everybody meets: all bin-steps < bs are complete and none >= bs has begun
-                    if (b == bs && b > 0) { flow_bar<K>(b - 1, handover); waited = true; }
-                    __syncthreads();
-                    if (need_hi - need_lo + 1 > R && threadIdx.x == 0) atomicCAS(status, 0u, 0xE1000000u | (unsigned)u);
-                    for (int e = lo; e < need_lo; ++e) // rows the chain has left: back to global memory
-                        if (e >= Q - 1 && e < T + Q - 1)
-                            for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
-                    __syncthreads();
-                    for (int e = hi + 1; e <= need_hi; ++e) // rows the chain is about to reach
-                        for (int x = threadIdx.x; x < Np; x += nall) ring[(size_t)(e & rmask) * pitch + x] = E0[(long long)e * P + x];
-                    __syncthreads();
-                }
-                if (need_hi > hi) { lo = need_lo; hi = need_hi; }
+                // drain: the role of bin-step bs takes its hand-over first (the committers of bs - 1 wait for it), then
+                // everybody meets: all bin-steps < bs are complete and none >= bs has begun
+                if (bmod == 0 && b > 0) { flow_bar(bar_prev, handover); waited = true; }
+                __syncthreads();
+                if (need_hi - need_lo + 1 > R && threadIdx.x == 0) atomicCAS(status, 0u, 0xE1000000u | (unsigned)u);
+                for (int e = lo; e < need_lo; ++e) // rows the chain has left: back to global memory
+                    if (e >= Q - 1 && e < T + Q - 1)
+                        for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+                __syncthreads();
+                for (int e = hi + 1; e <= need_hi; ++e) // rows the chain is about to reach
+                    for (int x = threadIdx.x; x < Np; x += nall) ring[(size_t)(e & rmask) * pitch + x] = E0[(long long)e * P + x];
+                __syncthreads();
+                lo = need_lo; hi = need_hi;
             }
         }
-        // the row update this lane works on: j = jhi - d, d = (jhi - tix) mod nt kept incrementally (K <= S: jhi grows by <= 1)
-        const long long jhi = b / S;
-        d += (int)(jhi - jhi_prev); if (d >= nt) d -= nt;
-        jhi_prev = jhi;
+        // the row update this lane works on: j = jhi - d, d = (jhi - tix) mod nt, on bin c = b - S j = bmod + S d
         const long long j = jhi - d;
+        const int c = bmod + S * d;
+        int ctl = (b + K <= bend ? 1 : 0) | (b < bend ? 2 : 0) | (b > 0 && !waited ? 4 : 0); // decided before the chain, not after it
+        asm volatile("" : "+r"(ctl));
+        const bool more = ctl & 1, handoff = ctl & 2, take = ctl & 4;
         bool act = false;
-        int c = 0;
         double a = 0.0;
-        if (j >= 0 && j < n) {
-            c = (int)(b - (long long)S * j);
-            if (c < Nreal) {
-                const int p = c % Q;
-                if (j != jc || p != pc) {
-                    LwsbOnlineTask task = lwsb_online_decode(T, iters, LA, Q, j);
-                    if (j != jc) {
-                        thr = task.thr < 0 ? 0.0 : __dmul_rn(thresholds[task.thr], mean); // lws.pyx:361, lwslib.cpp:1467
-                        a = __ldg(A0 + (long long)task.row * P + L + c);
-                    } else a = a_next;
-                    jc = j; pc = p;
-                    row = task.row; cframe = task.cframe;
-                    const int pn = (Q - p) % Q;
-                    const bool odd = FOLD == LWSB_FOLD_Q4 && (p & 1);
-                    off_own = (row & rmask) * pitch;
-                    wofs_c = ((task.which * Q + p) * Q + 0) * (L + 1);
-                    flg_c = cframe ? wf[(task.which * Q + p) * Q + 0] : 0u;
-#pragma unroll
-                    for (int s = 0; s < NP; ++s) {
-                        // the frame pairs in the order the reference adds them: odd bins of the Q4 folding take r = 1, 3
-                        // (sign-flipped) then 2 (lwslib.cpp:953-1052)
-                        const int r = odd ? (s == 0 ? 1 : (s == 1 ? 3 : 2)) : s + 1;
-                        sgn[s] = (odd && s < 2) ? 0x80000000u : 0u;
-                        off_m[s] = ((row - r) & rmask) * pitch;
-                        off_p[s] = r < task.rframe ? ((row + r) & rmask) * pitch : R * pitch; // R * pitch: the zero row
-                        wofs[s] = ((task.which * Q + p) * Q + r) * (L + 1);
-                        wofs_n[s] = ((task.which * Q + pn) * Q + r) * (L + 1);
-                        flg[s] = wf[(task.which * Q + p) * Q + r];
-                        flg_n[s] = wf[(task.which * Q + pn) * Q + r];
-                    }
+        if (j >= 0 && j < n && c < Nreal) {
+            const int p = c % Q;
+            if (j != jc || p != pc) {
+                LwsbOnlineTask task = lwsb_online_decode(T, iters, LA, Q, j);
+                if (j != jc) {
+                    thr = task.thr < 0 ? 0.0 : __dmul_rn(thresholds[task.thr], mean); // lws.pyx:361, lwslib.cpp:1467
+                    a = __ldg(A0 + (long long)task.row * P + L + c);
                 } else a = a_next;
-                if (c + K < Nreal) a_next = __ldg(A0 + (long long)row * P + L + c + K); // this lane's next bin
-                act = a > thr; // lwslib.cpp:295-296
-            }
+                jc = j; pc = p;
+                row = task.row;
+                const int pn = (Q - p) % Q;
+                const bool odd = FOLD == LWSB_FOLD_Q4 && (p & 1);
+                off_own = (unsigned)((row & rmask) * pitch) * 16u;
+                wofs_c = (unsigned)((task.which * Q + p) * WB) * 16u;
+                flg_c = task.cframe ? wf[(task.which * Q + p) * Q + 0] : 0u;
+#pragma unroll
+                for (int s = 0; s < NP; ++s) {
+                    // the frame pairs in the order the reference adds them: odd bins of the Q4 folding take r = 1, 3
+                    // (sign-flipped) then 2 (lwslib.cpp:953-1052)
+                    const int r = odd ? (s == 0 ? 1 : (s == 1 ? 3 : 2)) : s + 1;
+                    sgn[s] = (odd && s < 2) ? 0x80000000u : 0u;
+                    off_m[s] = (unsigned)(((row - r) & rmask) * pitch) * 16u;
+                    off_p[s] = (unsigned)(r < task.rframe ? ((row + r) & rmask) * pitch : R * pitch) * 16u; // R * pitch: the zero row
+                    wofs[s] = (unsigned)((task.which * Q + p) * WB + r * (L + 1)) * 16u;
+                    wofs_n[s] = (unsigned)((task.which * Q + pn) * WB + r * (L + 1)) * 16u;
+                    flg[s] = wf[(task.which * Q + p) * Q + r];
+                    flg_n[s] = wf[(task.which * Q + pn) * Q + r];
+                }
+            } else a = a_next;
+            if (c + K < Nreal) a_next = __ldg(A0 + (long long)row * P + L + c + K); // this lane's next bin
+            act = a > thr; // lwslib.cpp:295-296
         }
-        // ---- term values of the other frames, centre-frame values k >= K
-        const int col = L + c;
-        const bool edge = c <= 2 * L || c >= Nreal - 1 - 2 * L;
+        // ---- term values of the other frames
+        const unsigned colb = (unsigned)(L + c) * 16u;
+        const unsigned a_own = ring_s + off_own + colb, a_wc = w2_s + wofs_c;
         OnlineVals<Q, FOLD> vals;
-        double cvr[L], cvi[L];
-        double2 wc[K < L ? K : L]; // centre weights k < K, fetched before the hand-over
-        const double2 *own = ring + off_own + col;
+        double2 wc[L]; // centre weights, fetched before the hand-over
         if (act) {
 #pragma unroll
             for (int s = 0; s < NP; ++s) {
-                const double2 *pm = ring + off_m[s] + col, *pp = ring + off_p[s] + col, *ws = w2 + wofs[s];
+                const unsigned am = ring_s + off_m[s] + colb, ap = ring_s + off_p[s] + colb, aw = w2_s + wofs[s], awn = w2_s + wofs_n[s];
                 const int base = s * PER_R;
                 {
-                    const double2 bb = pm[0], cc = pp[0], ww = ws[0];
+                    const double2 bb = flow_ld<0>(am), cc = flow_ld<0>(ap), ww = flow_ld<0>(aw);
                     double vr, vi;
                     online_value(ww.x, ww.y, bb.x, bb.y, cc.x, cc.y, vr, vi);
                     vals.r[base] = flow_keep(vr, flg[s] & 1u); vals.i[base] = flow_keep(vi, flg[s] & 1u);
                 }
-#pragma unroll
-                for (int k = 1; k <= L; ++k) {
-                    const double2 e1 = pm[-k], e4 = pm[k], e2 = pp[k], e3 = pp[-k], ww = ws[k];
+                flow_for<1, L + 1>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    const double2 e1 = flow_ld<-k>(am), e4 = flow_ld<k>(am), e2 = flow_ld<k>(ap), e3 = flow_ld<-k>(ap), ww = flow_ld<k>(aw);
                     const bool keep = (flg[s] >> k) & 1u;
-                    if (FOLD == LWSB_FOLD_ANY) {
-                        const double2 wn = (w2 + wofs_n[s])[k];
+                    if constexpr (FOLD == LWSB_FOLD_ANY) {
+                        const double2 wn = flow_ld<k>(awn);
                         const bool keepn = (flg_n[s] >> k) & 1u;
                         double vr, vi;
                         online_value(ww.x, ww.y, e1.x, e1.y, e3.x, e3.y, vr, vi);
@@ -701,32 +716,22 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
                         online_value(ww.x, ww.y, br, bi, cr, ci, vr, vi);
                         vals.r[base + k] = flow_keep(vr, keep); vals.i[base + k] = flow_keep(vi, keep);
                     }
-                }
+                });
             }
-#pragma unroll
-            for (int k = 1; k <= L; ++k) {
-                if (k < K) wc[k - 1] = (w2 + wofs_c)[k];
-                else if (!edge) {
-                    const double2 bb = own[-k], cc = own[k], ww = (w2 + wofs_c)[k];
-                    double vr, vi;
-                    online_value(ww.x, ww.y, bb.x, bb.y, cc.x, cc.y, vr, vi);
-                    cvr[k - 1] = flow_keep(vr, (flg_c >> k) & 1u); cvi[k - 1] = flow_keep(vi, (flg_c >> k) & 1u);
-                }
-            }
+            flow_for<1, L + 1>([&](auto kc) { constexpr int k = decltype(kc)::value; wc[k - 1] = flow_ld<k>(a_wc); });
         }
         __syncwarp();
-        if (b > 0 && !waited) flow_bar<K>(b - 1, handover); // every bin of bin-step b - 1 is committed
-        // ---- the chain: centre-frame values k < K, the sum in the reference's order, projection, commit
+        if (take) flow_bar(bar_prev, handover); // every bin of bin-step b - 1 is committed
+        // ---- the chain: centre-frame values, the sum in the reference's order, projection, commit
         if (act) {
-#pragma unroll
-            for (int k = 1; k <= L; ++k)
-                if (k < K || edge) {
-                    const double2 bb = own[-k], cc = own[k];
-                    const double2 ww = k < K ? wc[k - 1] : (w2 + wofs_c)[k];
-                    double vr, vi;
-                    online_value(ww.x, ww.y, bb.x, bb.y, cc.x, cc.y, vr, vi);
-                    cvr[k - 1] = flow_keep(vr, (flg_c >> k) & 1u); cvi[k - 1] = flow_keep(vi, (flg_c >> k) & 1u);
-                }
+            double cvr[L], cvi[L];
+            flow_for<1, L + 1>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                const double2 bb = flow_ld<-k>(a_own), cc = flow_ld<k>(a_own);
+                double vr, vi;
+                online_value(wc[k - 1].x, wc[k - 1].y, bb.x, bb.y, cc.x, cc.y, vr, vi);
+                cvr[k - 1] = flow_keep(vr, (flg_c >> k) & 1u); cvi[k - 1] = flow_keep(vi, (flg_c >> k) & 1u);
+            });
             double tr = 0.0, ti = 0.0;
 #pragma unroll
             for (int k = 0; k < L; ++k) { tr = __dadd_rn(tr, cvr[k]); ti = __dadd_rn(ti, cvi[k]); }
@@ -734,14 +739,16 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
             for (int i = 0; i < OnlineVals<Q, FOLD>::N; ++i) { tr = __dadd_rn(tr, vals.r[i]); ti = __dadd_rn(ti, vals.i[i]); }
             double2 val;
             if (x_project(tr, ti, a, val)) {
-                double2 *Rrow = ring + off_own;
-                Rrow[L + c] = val;
-                if (c >= 1 && c <= L) Rrow[L - c] = make_double2(val.x, -val.y);
-                else if (c >= Nreal - 1 - L && c <= Nreal - 2) Rrow[L + 2 * (Nreal - 1) - c] = make_double2(val.x, -val.y);
+                flow_st(a_own, val.x, val.y);
+                if (c >= 1 && c <= L) flow_st(a_own - 32u * (unsigned)c, val.x, -val.y);                  // column L - c
+                else if (c >= Nreal - 1 - L && c <= Nreal - 2) flow_st(a_own + 32u * (unsigned)(Nreal - 1 - c), val.x, -val.y); // L + 2 (Nreal - 1) - c
             }
         }
         __syncwarp();
-        if (b < bend) flow_bar<K>(b, handover);
+        if (handoff) flow_bar(bar_mine, handover);
+        if (!more) break;
+        bmod += K;
+        if (bmod >= S) { bmod -= S; ++jhi; if (++d == nt) d = 0; }
     }
     __syncthreads();
     for (int e = lo; e <= hi; ++e)
@@ -957,9 +964,14 @@ bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const d
                     if (T_host[b] != lastTf) { lastTf = T_host[b]; spanf = std::max(spanf, online_max_span(lastTf, v.Nreal, Sf, Q, iters, LA)); }
                 int Rf = 8;
                 while (Rf < spanf) Rf *= 2;
+                // the lanes of a warp are on consecutive row updates: columns S apart, frames cycling through the look-ahead
+                // window.  With pitch = 2 (mod 8) cells and S = 9 the bank group advances by one from lane to lane whatever
+                // the look-ahead (2 frame - column), i.e. a half-warp's 16 cells fall two per bank group: no replays
+                const char *e_pm = getenv("LWSB_ONLINE_FLOW_PITCH");
+                const int pm = e_pm ? atoi(e_pm) & 7 : 2;
                 int pitchf = v.Nreal + 2 * OL;
-                if ((pitchf & 1) == 0) ++pitchf;
-                const size_t bytesf = (size_t)(Rf + 1) * pitchf * sizeof(double2) + (size_t)3 * Q * Q * ((OL + 1) * 16 + 4);
+                while ((pitchf & 7) != pm) ++pitchf;
+                const size_t bytesf = (size_t)(Rf + 1) * pitchf * sizeof(double2) + (size_t)3 * Q * ((Q * (OL + 1) + 1) * 16 + Q * 4);
                 if (bytesf + 1024 <= smem_limit) {
                     flowK = K; S = Sf;
                     switch (Q) {
