@@ -604,7 +604,7 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
     // loop invariants that sit between a commit and its hand-over: kept in registers (opaque to rematerialisation)
     asm volatile("" : "+r"(handover), "+r"(bar_mine), "+r"(bar_prev), "+l"(bend));
     int lo = 0, hi = -1;                                             // extended rows [lo, hi] are resident
-    long long jc = -1, jhi = 0;
+    long long jc = -1, jhi = 0, ev_j = 0;                            // ev_j: chain position at which the front reaches the next frame
     int bmod = role;                                                 // b mod S (role < K <= S)
     int d = (nt - tix) % nt;                                         // (jhi - tix) mod nt at jhi = 0
     // per-lane constants of the task (and of the residue of this role's bins): byte offsets into the ring / weight tables
@@ -617,12 +617,16 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
     double thr = 0.0, a_next = 0.0;
     for (long long b = role; b <= bend; b += K) {
         bool waited = false;
-        if (bmod < K) { // a multiple of S in (b - K, b]: the front of the chain reaches a new row update (each role sees each once)
+        // a multiple of S in (b - K, b]: the front of the chain reaches a new row update (each role sees each once); rows have
+        // to come in when that row update is the first of a frame
+        if (bmod < K && jhi >= ev_j) {
             const long long bs = b - bmod;
             const long long jh = min(jhi, n - 1);
             long long jlo = bs < Nreal ? 0 : (bs - (Nreal - 1) + S - 1) / S;
             if (jlo > n - 1) jlo = n - 1;
-            const int need_hi = min(Tp - 1, lwsb_online_frame(iters, LA, jh) + 2 * (Q - 1));
+            const int mfront = lwsb_online_frame(iters, LA, jh);
+            ev_j = mfront + 1 < T ? lwsb_online_frame_base(mfront + 1, iters, LA) : 0x7fffffffffffffffLL;
+            const int need_hi = min(Tp - 1, mfront + 2 * (Q - 1));
             if (need_hi > hi) {
                 const int need_lo = max(0, lwsb_online_frame(iters, LA, jlo) - LA);
                 // drain: the role of bin-step bs takes its hand-over first (the committers of bs - 1 wait for it), then
@@ -720,14 +724,18 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
             }
             flow_for<1, L + 1>([&](auto kc) { constexpr int k = decltype(kc)::value; wc[k - 1] = flow_ld<k>(a_wc); });
         }
-        __syncwarp();
+        // addresses of the commit, formed before the hand-over (and kept: opaque to rematerialisation)
+        unsigned a_cell = a_own, a_mir = a_own;
+        if (c >= 1 && c <= L) a_mir = a_own - 32u * (unsigned)c;                                      // column L - c
+        else if (c >= Nreal - 1 - L && c <= Nreal - 2) a_mir = a_own + 32u * (unsigned)(Nreal - 1 - c); // column L + 2 (Nreal - 1) - c
+        asm volatile("" : "+r"(a_cell), "+r"(a_mir));
         if (take) flow_bar(bar_prev, handover); // every bin of bin-step b - 1 is committed
         // ---- the chain: centre-frame values, the sum in the reference's order, projection, commit
         if (act) {
             double cvr[L], cvi[L];
             flow_for<1, L + 1>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                const double2 bb = flow_ld<-k>(a_own), cc = flow_ld<k>(a_own);
+                const double2 bb = flow_ld<-k>(a_cell), cc = flow_ld<k>(a_cell);
                 double vr, vi;
                 online_value(wc[k - 1].x, wc[k - 1].y, bb.x, bb.y, cc.x, cc.y, vr, vi);
                 cvr[k - 1] = flow_keep(vr, (flg_c >> k) & 1u); cvi[k - 1] = flow_keep(vi, (flg_c >> k) & 1u);
@@ -739,12 +747,10 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
             for (int i = 0; i < OnlineVals<Q, FOLD>::N; ++i) { tr = __dadd_rn(tr, vals.r[i]); ti = __dadd_rn(ti, vals.i[i]); }
             double2 val;
             if (x_project(tr, ti, a, val)) {
-                flow_st(a_own, val.x, val.y);
-                if (c >= 1 && c <= L) flow_st(a_own - 32u * (unsigned)c, val.x, -val.y);                  // column L - c
-                else if (c >= Nreal - 1 - L && c <= Nreal - 2) flow_st(a_own + 32u * (unsigned)(Nreal - 1 - c), val.x, -val.y); // L + 2 (Nreal - 1) - c
+                flow_st(a_cell, val.x, val.y);
+                if (a_mir != a_cell) flow_st(a_mir, val.x, -val.y);
             }
         }
-        __syncwarp();
         if (handoff) flow_bar(bar_mine, handover);
         if (!more) break;
         bmod += K;
