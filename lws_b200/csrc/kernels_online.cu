@@ -762,6 +762,199 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
             for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
 }
 
+#ifdef LWSB_EXPERIMENTS
+// ---------------------------------------------------------------- value warps and chain warps (Q <= 4, folded rules)
+// EXPERIMENT (round 2, -DLWSB_EXPERIMENTS and LWSB_ONLINE_RAIL=1): bit-exact, but 238 ms at configs[2] against 137 ms for
+// k_online_flow -- every instruction of the chain warp is on the critical path (1 330 cycles per bin with its bookkeeping, the
+// loads of 18 staged values and all five centre-frame values), and the value warps pay 80 register moves per bin to slide their
+// windows (profiles/r2_online_experiments.txt).
+// k_online_flow hands every bin of a task from one warp to the next: the bin committed one bin-step ago travels through shared
+// memory and a barrier on the critical path, and each of the K warps loads the whole 6 x 11 neighbourhood of its bin (ncu: the
+// shared-memory pipe of the busy SMs is ~75 % occupied, the loads of the chain queue behind them).  Here the work of a task
+// is split by KIND instead: per group of 32 tasks, warp r = 1 .. Q - 1 forms the term values of frame pair (m - r, m + r) for
+// EVERY bin of the task, and one chain warp runs the order-bound part of every bin.
+//   * A value warp keeps the 11 columns of its two rows in registers and slides them: two loads per bin instead of 22.  It
+//     runs one bin ahead of the chain warp and parks the 6 values of a bin in a staging area (two buffers, by parity of time).
+//   * The chain warp reads the 3 x 6 values, forms the centre-frame values, adds in the reference's order, projects, commits.
+//     The bin committed just before is the lane's own: it stays in a register, nothing is handed over.
+//   * One CTA barrier per bin-step; within a bin-step nobody reads a cell that somebody writes (see below).
+// Time t: value warps are on bin t - S j of task j, the chain warp on bin t - 1 - S j.  The values of bin c read columns
+// c - L .. c + L of the rows of earlier tasks: task j - 1 has committed through column c - 2 + S at the end of iteration t - 1,
+// so S >= L + 2; the new column of the sliding window, c + L, is one the chain warp of task j - 1 committed at iteration
+// t - 1 at the latest.  Cells written in iteration t (column c - 1 of the task's own row and its mirror cell) are read by no
+// value warp in iteration t: task j + 1 is S columns behind, task j - 1 S columns ahead, the own row is only read by the
+// chain lane itself.  Residue, kind of row update and the parity rule of the Q4 folding are per-lane data as in k_online_flow.
+template <int Q, int FOLD>
+__global__ void __launch_bounds__(256)
+k_online_rail(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *thresholds, int iters, int LA, int R, int pitch,
+              int S, unsigned *status)
+{
+    static_assert((Q == 4 && FOLD == LWSB_FOLD_Q4) || (Q == 2 && FOLD == LWSB_FOLD_Q2), "folded rules: 1 + L values per frame pair");
+    constexpr int L = OL, NP = Q - 1, PER_R = 1 + L, WB = Q * (L + 1) + 1, W11 = 2 * L + 1;
+    constexpr int SLOT = NP * PER_R + 1; // cells per task and buffer in the staging area (odd: consecutive lanes in different bank groups)
+    extern __shared__ __align__(16) unsigned char online_smem[];
+    double2 *ring = reinterpret_cast<double2 *>(online_smem);
+    double2 *zrow = ring + (size_t)R * pitch;
+    double2 *w2 = zrow + pitch;
+    const int nall = blockDim.x, G = nall / (32 * Q), nt = 32 * G;
+    double2 *stage = w2 + 3 * Q * WB;                                  // [2][nt][SLOT]
+    unsigned *wf = reinterpret_cast<unsigned *>(stage + 2 * nt * SLOT); // flags [3][Q][Q]
+    for (int i = threadIdx.x; i < 3 * Q * Q * (L + 1); i += blockDim.x)
+        w2[i / (Q * (L + 1)) * WB + i % (Q * (L + 1))] = make_double2((&w.wr[0][0][0][0])[i], (&w.wi[0][0][0][0])[i]);
+    for (int i = threadIdx.x; i < 3 * Q * Q; i += blockDim.x) wf[i] = (&w.flag[0][0][0])[i];
+    for (int i = threadIdx.x; i < pitch; i += blockDim.x) zrow[i] = make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < 2 * nt * SLOT; i += blockDim.x) stage[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring), w2_s = (unsigned)__cvta_generic_to_shared(w2);
+    const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
+    const int u = blockIdx.x;
+    const int T = v.T[u], Nreal = v.Nreal, P = v.P;
+    const int Np = Nreal + 2 * L, Tp = T + 2 * (Q - 1), rmask = R - 1;
+    double2 *E0 = v.E + v.rowbase[u] * (long long)P + (v.c0 - L);
+    const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
+    const double mean = v.mean_amp[u];
+    const long long n = lwsb_online_chain_len(T, iters, LA);
+    const long long tend = (long long)S * (n - 1) + (Nreal - 1) + 1;   // the chain warp is one iteration behind
+    const int wid = threadIdx.x >> 5, role = wid / G, tix = (wid % G) * 32 + (threadIdx.x & 31);
+    const bool chain = role == NP;
+    const int r = role + 1;                                            // frame pair of a value warp
+    const int lag = chain ? 1 : 0;                                     // local time tl = t - lag; the lane is on bin tl - S j
+    int lo = 0, hi = -1;
+    long long jhi = 0, ev_j = 0;                                       // jhi = tl / S (>= 0), ev_j: see k_online_flow
+    long long jf = 0;                                                  // t / S: the front of the value warps (residency)
+    int tmod = 0, fmod = 0;                                            // tl mod S, t mod S
+    int d = (nt - tix) % nt;
+    // value warps: the two rows of the frame pair, columns c - L .. c + L
+    double2 wm[W11], wp[W11];
+#pragma unroll
+    for (int i = 0; i < W11; ++i) wm[i] = wp[i] = make_double2(0.0, 0.0);
+    unsigned off_m = 0, off_p = 0, wtask = 0, flags4 = 0;              // flags4: the 1 + L flag bits of residues 0 .. Q - 1, 8 bits each
+    // chain warp
+    unsigned off_own = 0, wtask_c = 0, flags_c4 = 0;
+    int row = Q - 1;
+    double thr = 0.0, a_next = 0.0;
+    for (long long t = 0; t <= tend; ++t) {
+        if (fmod == 0 && jf >= ev_j) { // the front reaches a new row update, the first of a frame: rows come in, rows the tail has left go out
+            const long long jh = min(jf, n - 1);
+            const long long tc = t - 1; // time of the chain warp, which is still to run this iteration
+            long long jlo = tc < Nreal ? 0 : (tc - (Nreal - 1) + S - 1) / S;
+            if (jlo > n - 1) jlo = n - 1;
+            const int mfront = lwsb_online_frame(iters, LA, jh);
+            ev_j = mfront + 1 < T ? lwsb_online_frame_base(mfront + 1, iters, LA) : 0x7fffffffffffffffLL;
+            const int need_hi = min(Tp - 1, mfront + 2 * (Q - 1));
+            if (need_hi > hi) {
+                const int need_lo = max(0, lwsb_online_frame(iters, LA, jlo) - LA);
+                if (need_hi - need_lo + 1 > R && threadIdx.x == 0) atomicCAS(status, 0u, 0xE1000000u | (unsigned)u);
+                for (int e = lo; e < need_lo; ++e)
+                    if (e >= Q - 1 && e < T + Q - 1)
+                        for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+                __syncthreads();
+                for (int e = hi + 1; e <= need_hi; ++e)
+                    for (int x = threadIdx.x; x < Np; x += nall) ring[(size_t)(e & rmask) * pitch + x] = E0[(long long)e * P + x];
+                __syncthreads();
+                lo = need_lo; hi = need_hi;
+            }
+        }
+        const bool started = t >= lag;
+        const long long j = jhi - d;
+        const int c = tmod + S * d;
+        const bool on = started && j >= 0 && j < n && c < Nreal;
+        const unsigned buf_v = (unsigned)(t & 1), buf_c = buf_v ^ 1u;
+        if (!chain) {
+            if (on) {
+                if (c == 0) { // a new task: its rows, weights and flags; the whole window
+                    const LwsbOnlineTask task = lwsb_online_decode(T, iters, LA, Q, j);
+                    off_m = (unsigned)(((task.row - r) & rmask) * pitch) * 16u;
+                    off_p = (unsigned)(r < task.rframe ? ((task.row + r) & rmask) * pitch : R * pitch) * 16u;
+                    wtask = (unsigned)(task.which * Q * WB + r * (L + 1)) * 16u;
+                    flags4 = 0;
+#pragma unroll
+                    for (int pp = 0; pp < Q; ++pp) flags4 |= (wf[(task.which * Q + pp) * Q + r] & 0xffu) << (8 * pp);
+                    const unsigned am = ring_s + off_m + (unsigned)L * 16u, ap = ring_s + off_p + (unsigned)L * 16u;
+                    flow_for<0, W11>([&](auto ic) { constexpr int i = decltype(ic)::value; wm[i] = flow_ld<i - L>(am); wp[i] = flow_ld<i - L>(ap); });
+                } else {
+#pragma unroll
+                    for (int i = 0; i + 1 < W11; ++i) { wm[i] = wm[i + 1]; wp[i] = wp[i + 1]; }
+                    const unsigned colb = (unsigned)(L + c + L) * 16u;
+                    wm[W11 - 1] = flow_ld<0>(ring_s + off_m + colb); wp[W11 - 1] = flow_ld<0>(ring_s + off_p + colb);
+                }
+                const int p = c % Q;
+                const unsigned aw = w2_s + wtask + (unsigned)(p * WB) * 16u;
+                const unsigned flg = (flags4 >> (8 * p)) & 0xffu;
+                const unsigned sgn = (FOLD == LWSB_FOLD_Q4 && (p & 1) && r != 2) ? 0x80000000u : 0u;
+                const unsigned ast = stage_s + (unsigned)(((int)buf_v * nt + tix) * SLOT + (r - 1) * PER_R) * 16u;
+                {
+                    const double2 ww = flow_ld<0>(aw);
+                    double vr, vi;
+                    online_value(ww.x, ww.y, wm[L].x, wm[L].y, wp[L].x, wp[L].y, vr, vi);
+                    flow_st(ast, flow_keep(vr, flg & 1u), flow_keep(vi, flg & 1u));
+                }
+                flow_for<1, L + 1>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    const double2 e1 = wm[L - k], e4 = wm[L + k], e2 = wp[L + k], e3 = wp[L - k], ww = flow_ld<k>(aw);
+                    const bool keep = (flg >> k) & 1u;
+                    // b = e1 -+ e2, c = e3 -+ e4 (lwslib.cpp:204-207, 228-231): x - y == x + (-y) bit for bit
+                    const double br = __dadd_rn(e1.x, flow_flip(e2.x, sgn)), bi = __dadd_rn(e1.y, flow_flip(e2.y, sgn));
+                    const double cr = __dadd_rn(e3.x, flow_flip(e4.x, sgn)), ci = __dadd_rn(e3.y, flow_flip(e4.y, sgn));
+                    double vr, vi;
+                    online_value(ww.x, ww.y, br, bi, cr, ci, vr, vi);
+                    flow_st(ast + 16u * k, flow_keep(vr, keep), flow_keep(vi, keep));
+                });
+            }
+        } else if (on) {
+            double a;
+            if (c == 0) {
+                const LwsbOnlineTask task = lwsb_online_decode(T, iters, LA, Q, j);
+                thr = task.thr < 0 ? 0.0 : __dmul_rn(thresholds[task.thr], mean); // lws.pyx:361, lwslib.cpp:1467
+                row = task.row;
+                off_own = (unsigned)((row & rmask) * pitch) * 16u;
+                wtask_c = (unsigned)(task.which * Q * WB) * 16u;
+                flags_c4 = 0;
+                if (task.cframe) {
+#pragma unroll
+                    for (int pp = 0; pp < Q; ++pp) flags_c4 |= (wf[(task.which * Q + pp) * Q + 0] & 0xffu) << (8 * pp);
+                }
+                a = __ldg(A0 + (long long)row * P + L + c);
+            } else a = a_next;
+            if (c + 1 < Nreal) a_next = __ldg(A0 + (long long)row * P + L + c + 1);
+            if (a > thr) { // lwslib.cpp:295-296
+                const int p = c % Q;
+                const bool odd = FOLD == LWSB_FOLD_Q4 && (p & 1);
+                const unsigned a_cell = ring_s + off_own + (unsigned)(L + c) * 16u, a_wc = w2_s + wtask_c + (unsigned)(p * WB) * 16u;
+                const unsigned flg_c = (flags_c4 >> (8 * p)) & 0xffu;
+                const unsigned ast = stage_s + (unsigned)(((int)buf_c * nt + tix) * SLOT) * 16u;
+                // the frame pairs in the order the reference adds them: odd bins of the Q4 folding take r = 1, 3 then 2 (lwslib.cpp:953-1052)
+                const unsigned as1 = ast + (unsigned)((odd ? 2 : 1) * PER_R) * 16u, as2 = ast + (unsigned)((odd ? 1 : 2) * PER_R) * 16u;
+                double tr = 0.0, ti = 0.0;
+                flow_for<1, L + 1>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    const double2 bb = flow_ld<-k>(a_cell), cc = flow_ld<k>(a_cell), ww = flow_ld<k>(a_wc);
+                    double vr, vi;
+                    online_value(ww.x, ww.y, bb.x, bb.y, cc.x, cc.y, vr, vi);
+                    tr = __dadd_rn(tr, flow_keep(vr, (flg_c >> k) & 1u)); ti = __dadd_rn(ti, flow_keep(vi, (flg_c >> k) & 1u));
+                });
+                flow_for<0, PER_R>([&](auto kc) { const double2 x = flow_ld<decltype(kc)::value>(ast); tr = __dadd_rn(tr, x.x); ti = __dadd_rn(ti, x.y); });
+                if constexpr (NP > 1) flow_for<0, PER_R>([&](auto kc) { const double2 x = flow_ld<decltype(kc)::value>(as1); tr = __dadd_rn(tr, x.x); ti = __dadd_rn(ti, x.y); });
+                if constexpr (NP > 2) flow_for<0, PER_R>([&](auto kc) { const double2 x = flow_ld<decltype(kc)::value>(as2); tr = __dadd_rn(tr, x.x); ti = __dadd_rn(ti, x.y); });
+                double2 val;
+                if (x_project(tr, ti, a, val)) {
+                    flow_st(a_cell, val.x, val.y);
+                    if (c >= 1 && c <= L) flow_st(a_cell - 32u * (unsigned)c, val.x, -val.y);                                            // column L - c
+                    else if (c >= Nreal - 1 - L && c <= Nreal - 2) flow_st(a_cell + 32u * (unsigned)(Nreal - 1 - c), val.x, -val.y); // L + 2 (Nreal - 1) - c
+                }
+            }
+        }
+        __syncthreads();
+        if (started) { if (++tmod == S) { tmod = 0; ++jhi; if (++d == nt) d = 0; } }
+        if (++fmod == S) { fmod = 0; ++jf; }
+    }
+    for (int e = lo; e <= hi; ++e)
+        if (e >= Q - 1 && e < T + Q - 1)
+            for (int x = threadIdx.x; x < Np; x += nall) E0[(long long)e * P + x] = ring[(size_t)(e & rmask) * pitch + x];
+}
+
+#endif // LWSB_EXPERIMENTS
+
 template <int Q, int FOLD, int P>
 __device__ __forceinline__ void online_sum_for_residue(int p, const OnlineRingCell &E, const OnlineW<Q> &w, int ws, int rframe,
                                                        int cframe, double &tr, double &ti)
@@ -856,13 +1049,13 @@ k_online_ring(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
 
 // Largest number of extended rows resident at once: rows are loaded when the front of the chain first needs
 // them (at steps t = k*S) and rows behind the tail are dropped at the same moment -- same formulas as the kernel.
-int online_max_span(int T, int Nreal, int S, int Q, int iters, int LA)
+int online_max_span(int T, int Nreal, int S, int Q, int iters, int LA, int lag = 0)
 {
     const long long n = lwsb_online_chain_len(T, iters, LA);
     const int Tp = T + 2 * (Q - 1);
     int span = 0;
     for (long long k = 0; k < n; ++k) {
-        const long long t = k * S;
+        const long long t = k * S - lag; // the tail (k_online_rail: its chain warps) is `lag` iterations behind the front
         long long jl = t < Nreal ? 0 : (t - (Nreal - 1) + S - 1) / S;
         if (jl > n - 1) jl = n - 1;
         const int hi = std::min(Tp - 1, lwsb_online_frame(iters, LA, k) + 2 * (Q - 1));
@@ -877,6 +1070,20 @@ cudaError_t launch_t(const LwsbView &v, const OnlineW<Q> &w, const double *thr, 
                      size_t bytes, size_t smem_limit, unsigned *status, int *which_kernel, int flowK, cudaStream_t s)
 {
     *which_kernel = 1;
+#ifdef LWSB_EXPERIMENTS
+    if constexpr ((Q == 4 && FOLD == LWSB_FOLD_Q4) || (Q == 2 && FOLD == LWSB_FOLD_Q2)) {
+        if (flowK < 0) { // value warps and chain warps; `nt` is the CTA size, `bytes` includes zero row, weights and staging area
+            auto kern5 = k_online_rail<Q, FOLD>;
+            if (bytes > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                if (e != cudaSuccess) return e;
+            }
+            kern5<<<v.B, nt, bytes, s>>>(v, w, thr, iters, LA, R, pitch, S, status);
+            *which_kernel = 5;
+            return cudaGetLastError();
+        }
+    }
+#endif
     if constexpr (Q <= 4) {
         if (flowK > 0) { // K warps per task taking turns; `nt` is the CTA size, `bytes` includes the zero row and the weights
             auto kern4 = flowK == 4 ? k_online_flow<Q, FOLD, 4> : (flowK == 3 ? k_online_flow<Q, FOLD, 3> : k_online_flow<Q, FOLD, 2>);
@@ -957,6 +1164,34 @@ bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const d
     // step on the same residue, and the bins a task takes in one step stay clear of its neighbours' in the chain
     int S = Q <= 4 ? (OL + 2 + Q - 1) / Q * Q : (OL + 1 + Q - 1) / Q * Q;
     int flowK = 0;
+#ifdef LWSB_EXPERIMENTS
+    if (Q <= 4 && (fold == LWSB_FOLD_Q4 || fold == LWSB_FOLD_Q2)) { // k_online_rail: value warps + chain warps (LWSB_ONLINE_RAIL=1 enables, LWSB_ONLINE_RAIL_S: the lag)
+        const char *e_rail = getenv("LWSB_ONLINE_RAIL"), *e_s = getenv("LWSB_ONLINE_RAIL_S"), *e_pm = getenv("LWSB_ONLINE_FLOW_PITCH");
+        if (e_rail && atoi(e_rail) == 1) {
+            const int Sr = std::max(OL + 2, e_s ? atoi(e_s) : 9);
+            const int tasks = (v.Nreal + Sr - 1) / Sr + 2, G = (tasks + 31) / 32;
+            if (G * Q * 32 <= 256) {
+                int spanr = 0, lastTr = -1;
+                for (int b = 0; b < v.B; ++b)
+                    if (T_host[b] != lastTr) { lastTr = T_host[b]; spanr = std::max(spanr, online_max_span(lastTr, v.Nreal, Sr, Q, iters, LA, 1)); }
+                int Rr = 8;
+                while (Rr < spanr) Rr *= 2;
+                const int pm = e_pm ? atoi(e_pm) & 7 : 2; // see k_online_flow below: consecutive lanes in consecutive bank groups
+                int pitchr = v.Nreal + 2 * OL;
+                while ((pitchr & 7) != pm) ++pitchr;
+                const size_t bytesr = (size_t)(Rr + 1) * pitchr * sizeof(double2) + (size_t)3 * Q * (Q * (OL + 1) + 1) * 16 +
+                                      (size_t)2 * (32 * G) * ((Q - 1) * (OL + 1) + 1) * 16 + (size_t)3 * Q * Q * 4;
+                if (bytesr + 1024 <= smem_limit) {
+                    switch (Q) {
+                    case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, Rr, pitchr, Sr, G * Q * 32, bytesr, smem_limit, status, which_kernel, -1, s); break;
+                    case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, Rr, pitchr, Sr, G * Q * 32, bytesr, smem_limit, status, which_kernel, -1, s); break;
+                    }
+                    return true;
+                }
+            }
+        }
+    }
+#endif
     if (Q <= 4) { // k_online_flow: K warps per task, any lag S >= K + L (LWSB_ONLINE_FLOW=0 disables, =2/3 sets K; LWSB_ONLINE_FLOW_S the lag)
         const char *e_flow = getenv("LWSB_ONLINE_FLOW"), *e_s = getenv("LWSB_ONLINE_FLOW_S");
         int K = e_flow ? atoi(e_flow) : 4;

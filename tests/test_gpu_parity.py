@@ -347,15 +347,19 @@ def test_online_ring_kernels(gpu, oracle, fs, hop, la, its, n):
         _close(pg.online_lws(As[0][:T]), po.online_lws(As[0][:T]), "online T=%d" % T)
 
 
-@pytest.mark.parametrize("flow,lag,want", [("0", None, 3), ("2", None, 4), ("3", None, 4), ("4", "10", 4), ("4", "13", 4)])
+_RAIL = lambda lag: pytest.param({"LWSB_ONLINE_RAIL": "1", "LWSB_ONLINE_RAIL_S": lag}, 5, 4, marks=needs_experiments)
+
+
+@pytest.mark.parametrize("env,want,want_any", [({"LWSB_ONLINE_FLOW": "0"}, 3, 3), ({"LWSB_ONLINE_FLOW": "2"}, 4, 4), ({"LWSB_ONLINE_FLOW": "3"}, 4, 4),
+                                               ({"LWSB_ONLINE_FLOW_S": "10"}, 4, 4), ({"LWSB_ONLINE_FLOW_S": "13"}, 4, 4),
+                                               _RAIL("7"), _RAIL("9"), _RAIL("12")])
 @pytest.mark.parametrize("fs,hop,la,its", [(512, 128, 3, 4), (128, 64, 2, 5)])
-def test_online_kernel_choices(gpu, oracle, monkeypatch, flow, lag, want, fs, hop, la, its):
-    """The other shapes of the online chain kernel -- two lanes per task (LWSB_ONLINE_FLOW=0), 2 or 3 warps per task, longer
-    lags between row updates -- give the same bits."""
+def test_online_kernel_choices(gpu, oracle, monkeypatch, env, want, want_any, fs, hop, la, its):
+    """The other shapes of the online chain kernel -- two lanes per task, 2 or 3 warps per task taking turns, longer lags between
+    row updates, and (experiments build) value warps + chain warps -- give the same bits."""
     from lws_b200 import api
-    monkeypatch.setenv("LWSB_ONLINE_FLOW", flow)
-    if lag:
-        monkeypatch.setenv("LWSB_ONLINE_FLOW_S", lag)
+    for k, val in env.items():
+        monkeypatch.setenv(k, val)
     kw = dict(look_ahead=la, online_iterations=its)
     po, pg = oracle.lws(fs, hop, **kw), gpu.lws(fs, hop, **kw)
     As = [np.abs(po.stft(make_signal(k, 77 + i, 7000 + 900 * i))) for i, k in enumerate(("white", "tonal"))]
@@ -363,14 +367,14 @@ def test_online_kernel_choices(gpu, oracle, monkeypatch, flow, lag, want, fs, ho
         Ys = pg.online_lws(As, thresholds=thr)
         assert api._context(0).last_online_kernel() == want
         for A, Y in zip(As, Ys):
-            _close(Y, po.online_lws(A, thresholds=thr), "online kernel flow=%s lag=%s" % (flow, lag))
-    # the anyQ formulas on the same kernel (LWSB_FORCE_ANYQ) against the oracle made to take its anyQ branch
+            _close(Y, po.online_lws(A, thresholds=thr), "online kernel %s" % env)
+    # the anyQ formulas (LWSB_FORCE_ANYQ) against the oracle made to take its anyQ branch
     from lws_b200 import _native
     thr = np.ones(its)
     Yg = gpu.online_lws(As[0], pg.W, pg.W_ai, pg.W_af, thr, la, hop, flags=_native.FORCE_ANYQ)
-    assert api._context(0).last_online_kernel() == want
+    assert api._context(0).last_online_kernel() == want_any
     monkeypatch.setattr(oracle, "_fold", lambda Q, Qprime, simp, Nreal: 0)
-    _close(Yg, oracle.online_lws(As[0], po.W, po.W_ai, po.W_af, thr, la, hop), "online anyQ formulas, flow=%s" % flow)
+    _close(Yg, oracle.online_lws(As[0], po.W, po.W_ai, po.W_af, thr, la, hop), "online anyQ formulas, %s" % env)
 
 
 @pytest.mark.parametrize("fs,hop,kw,chunks", [(512, 128, {}, (1, 2, 3, 5, 8, 13, 40)), (64, 16, {"look_ahead": 0}, (7,)), (64, 8, {"look_ahead": 2}, (1, 30)),
