@@ -175,6 +175,30 @@ __device__ __forceinline__ bool x_project(double tr, double ti, double a, double
     return x > 0.0; // sqrt(x) > 0 iff x > 0
 }
 
+// x_project with the range checks of the fast paths replaced by a SUFFICIENT condition on the inputs, known before the square
+// root starts (so that it is not between the last division and the store): x in [2^-200, 2^900) and each numerator zero or
+// in [2^-500, 2^900) in magnitude => |temp| in [2^-100, 2^450], quotients in [2^-950, 2^1000]: every check of fm_sqrt /
+// fm_rcp / fm_div passes.  Anything else (denormal-scale or huge spectra) takes the library functions.  Same bits either way.
+__device__ __forceinline__ bool x_project_early(double tr, double ti, double a, double2 &out)
+{
+    const double x = __dadd_rn(__dmul_rn(tr, tr), __dmul_rn(ti, ti));
+    const double nr = __dmul_rn(tr, a), ni = __dmul_rn(ti, a);
+    constexpr unsigned LO_X = (unsigned)(1023 - 200) << 20, HI = (unsigned)(1023 + 900) << 20, LO_N = (unsigned)(1023 - 500) << 20;
+    const unsigned hx = (unsigned)__double2hiint(x), hr = (unsigned)__double2hiint(nr) & 0x7fffffffu, hi_ = (unsigned)__double2hiint(ni) & 0x7fffffffu;
+    const bool fast = (hx - LO_X) < (HI - LO_X) && ((hr - LO_N) < (HI - LO_N) || nr == 0.0) && ((hi_ - LO_N) < (HI - LO_N) || ni == 0.0);
+    if (fast) {
+        bool o1, o2, o3, o4;
+        const double mag = fm_sqrt(x, o1);
+        const double rcp = fm_rcp(mag, o2);
+        out.x = fm_div(nr, mag, rcp, o3);
+        out.y = fm_div(ni, mag, rcp, o4);
+        return true; // x >= 2^-200 > 0
+    }
+    const double mag = __dsqrt_rn(x);
+    out.x = __ddiv_rn(nr, mag); out.y = __ddiv_rn(ni, mag);
+    return x > 0.0;
+}
+
 // |z| as numpy computes it for a contiguous complex128 array on an FMA-capable x86-64
 // (numpy >= 1.25 CDOUBLE_absolute, SIMD path): max * sqrt(fma(q, q, 1)), q = min / max.
 // np.abs(ExtS) / np.abs(S) of lws.pyx:239-240 go through that loop; the oracle (numpy on the

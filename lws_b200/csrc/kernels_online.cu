@@ -596,9 +596,18 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
     const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
     const double mean = v.mean_amp[u];
     const long long n = lwsb_online_chain_len(T, iters, LA);
+    const int wmap = (S >> 16) & 3;
+    S &= 0xffff;
     long long bend = (long long)S * (n - 1) + (Nreal - 1) + 1; // one empty bin-step closes the last hand-over
     const int nall = blockDim.x, G = nall / (32 * K), nt = 32 * G;   // nt tasks in flight, K lanes each
-    const int wid = threadIdx.x >> 5, role = wid / G, tix = (wid % G) * 32 + (threadIdx.x & 31);
+    // warp w issues on scheduler w mod 4.  With two groups the warps of roles rho and rho + 1 share a pair of schedulers: the chain
+    // of bin-step b then runs next to a warp that is waiting for its own hand-over (b + 1) half of the time, instead of always next
+    // to one in the middle of its term values
+    const int wid = threadIdx.x >> 5;
+    int role = wid / G, grp = wid % G;
+    if (K == 4 && G == 2 && wmap == 1) { role = (wid >> 1) == 1 ? 2 : ((wid >> 1) == 2 ? 1 : (wid >> 1)); grp = wid & 1; }
+    if (K == 4 && wmap == 2) { role = wid & 3; grp = wid >> 2; } // both groups of a role on one scheduler
+    const int tix = grp * 32 + (threadIdx.x & 31);
     int handover = 2 * nt;                                           // threads on a hand-over barrier
     int bar_mine = 1 + role, bar_prev = 1 + (role + K - 1) % K;      // b mod K == role for every bin-step of this warp
     // loop invariants that sit between a commit and its hand-over: kept in registers (opaque to rematerialisation)
@@ -746,7 +755,7 @@ k_online_flow(LwsbView v, const __grid_constant__ OnlineW<Q> w, const double *th
 #pragma unroll
             for (int i = 0; i < OnlineVals<Q, FOLD>::N; ++i) { tr = __dadd_rn(tr, vals.r[i]); ti = __dadd_rn(ti, vals.i[i]); }
             double2 val;
-            if (x_project(tr, ti, a, val)) {
+            if (x_project_early(tr, ti, a, val)) {
                 flow_st(a_cell, val.x, val.y);
                 if (a_mir != a_cell) flow_st(a_mir, val.x, -val.y);
             }
@@ -1214,7 +1223,8 @@ bool launch_online_ring(const LwsbView &v, const double *const *wr_host, const d
                 while ((pitchf & 7) != pm) ++pitchf;
                 const size_t bytesf = (size_t)(Rf + 1) * pitchf * sizeof(double2) + (size_t)3 * Q * ((Q * (OL + 1) + 1) * 16 + Q * 4);
                 if (bytesf + 1024 <= smem_limit) {
-                    flowK = K; S = Sf;
+                    const char *e_map = getenv("LWSB_ONLINE_FLOW_MAP");
+                    flowK = K; S = Sf | (((e_map ? atoi(e_map) : 1) & 3) << 16);
                     switch (Q) {
                     case 2: *err = launch_q<2>(v, wr_host, wi_host, fold, thr, iters, LA, Rf, pitchf, S, G * K * 32, bytesf, smem_limit, status, which_kernel, flowK, s); break;
                     case 4: *err = launch_q<4>(v, wr_host, wi_host, fold, thr, iters, LA, Rf, pitchf, S, G * K * 32, bytesf, smem_limit, status, which_kernel, flowK, s); break;
