@@ -13,6 +13,7 @@
 // kernels_batch.cu.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include "lwsb_common.h"
 #include "kernels.h"
@@ -427,6 +428,115 @@ k_nofuture_q4(LwsbView v, const double *wr, const double *wi, const int *wf, con
     }
 }
 
+// The same sweep with its working set in shared memory (L = 5).  The global-memory kernel above issues the ~35 cell loads of
+// a bin one after the other behind its `continue`s (each an L2 round trip): 21 ms for one sweep over 64 x 628 frames, ~65 k
+// cycles per frame.  Here frames m-3 .. m live in a shared-memory window laid out exactly like the reference's flat buffer --
+// consecutive rows Np cells apart, so that "row m-r, offset 2n +- k" is one address plus an immediate whether or not the
+// offset runs into the next row: 8 row slots (rows m-3 .. m+1 are live) + a ninth that mirrors slot 0 (the row after slot 7).  Row m+1 and its amplitudes
+// are fetched with cp.async while frame m is processed; dropped terms (|W| <= 1e-12) are added as -0.0 (the running sum starts
+// at +0.0 and can never be -0.0: adding a zero of either sign leaves its bits), so a bin is straight-line code.
+template <int L>
+__global__ void __launch_bounds__(512)
+k_nofuture_q4_ring(LwsbView v, const double *wr, const double *wi, const int *wf, const double *thresholds, int iters)
+{
+    constexpr int Q = 4;
+    const int u = blockIdx.x;
+    const int T = v.T[u], Nreal = v.Nreal;
+    const int Np = Nreal + 2 * L, Naux = Nreal + L - 1, P = v.P;
+    extern __shared__ __align__(16) unsigned char nf_smem[];
+    constexpr int NS = 8;
+    double2 *win = reinterpret_cast<double2 *>(nf_smem);            // [NS + 1][Np]
+    double2 *w2 = win + (NS + 1) * Np;                                      // (wr, wi)[Q][Q][L + 1]
+    double *amp = reinterpret_cast<double *>(w2 + Q * Q * (L + 1)); // [2][Np + 1]
+    unsigned *keep = reinterpret_cast<unsigned *>(amp + 2 * (Np + 1)); // [Q][Q] bit k
+    for (int i = threadIdx.x; i < Q * Q * (L + 1); i += blockDim.x) w2[i] = make_double2(wr[i], wi[i]);
+    for (int i = threadIdx.x; i < Q * Q; i += blockDim.x) {
+        unsigned f = 0;
+        for (int k = 0; k <= L; ++k) f |= wf[i * (L + 1) + k] ? 1u << k : 0u;
+        keep[i] = f;
+    }
+    const double mean = v.mean_amp[u];
+    double2 *E0 = v.E + v.rowbase[u] * (long long)P + (v.c0 - L); // extended (row 0, column 0)
+    const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
+    const int lim1 = (Np - L + 1) / 2; // first n whose reads reach the current frame
+    auto fetch_row = [&](int row) { // extended row -> its slot (and the mirror of slot 0), amplitudes -> amp[row & 1]
+        const unsigned slot = (unsigned)(row & (NS - 1));
+        for (int x = threadIdx.x; x < Np; x += blockDim.x) {
+            const double2 *src = E0 + (long long)row * P + x;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(win + slot * Np + x)), "l"(src) : "memory");
+            if (slot == 0)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(win + NS * Np + x)), "l"(src) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(amp + (row & 1) * (Np + 1) + x)),
+                         "l"(A0 + (long long)row * P + x) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int it = 0; it < iters; ++it) {
+        const double thr = __dmul_rn(thresholds[it], mean); // lws.pyx:298
+        __syncthreads();
+        for (int row = 0; row < Q; ++row) fetch_row(row); // the ghost rows 0 .. Q-2 and the first frame
+        for (int m = Q - 1; m < T + Q - 1; ++m) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads(); // row m and its amplitudes are in; everybody is done with frame m-1
+            if (m + 1 < T + Q - 1) fetch_row(m + 1); // into the slot of row m-7
+            const double *arow = amp + (m & 1) * (Np + 1);
+            double2 *cur = win + (m & (NS - 1)) * Np, *cur_dup = (m & (NS - 1)) == 0 ? win + NS * Np : nullptr;
+            int done = L;
+            while (done <= Naux) {
+                int hi = (2 * L < done) ? (done + Np - L + 1) / 2 : lim1;
+                if (hi < done + 1) hi = done + 1;
+                if (hi > Naux + 1) hi = Naux + 1;
+                for (int n = done + threadIdx.x; n < hi; n += blockDim.x) {
+                    const double a = arow[n];
+                    if (!(a > thr)) continue;
+                    double tr = 0.0, ti = 0.0;
+                    const int pr = (n - L) & (Q - 1);
+                    const bool oddn = pr & 1;
+#pragma unroll
+                    for (int r = Q - 1; r > 0; --r) {
+                        const double2 *wrow = w2 + (pr * Q + r) * (L + 1);
+                        const unsigned kb = keep[pr * Q + r];
+                        const bool minus = oddn && (r & 1);
+                        const double2 *base = win + ((m - r) & (NS - 1)) * Np + 2 * n; // flat offset (m-r)*Np + 2n: may run into the next row
+#pragma unroll
+                        for (int k = 1; k <= L; ++k) {
+                            const double2 ww = wrow[k], b = base[-k];
+                            double2 c = base[k];
+                            if (minus) { c.x = -c.x; c.y = -c.y; }
+                            const double vr = __dsub_rn(__dmul_rn(ww.x, __dadd_rn(b.x, c.x)), __dmul_rn(ww.y, __dsub_rn(b.y, c.y)));
+                            const double vi = __dadd_rn(__dmul_rn(ww.x, __dadd_rn(b.y, c.y)), __dmul_rn(ww.y, __dsub_rn(b.x, c.x)));
+                            const bool kp = (kb >> k) & 1u;
+                            tr = __dadd_rn(tr, kp ? vr : -0.0); ti = __dadd_rn(ti, kp ? vi : -0.0);
+                        }
+                        {
+                            const double2 ww = wrow[0], b = base[0];
+                            const double vr = __dsub_rn(__dmul_rn(ww.x, b.x), __dmul_rn(ww.y, b.y));
+                            const double vi = __dadd_rn(__dmul_rn(ww.x, b.y), __dmul_rn(ww.y, b.x));
+                            const bool kp = kb & 1u;
+                            tr = __dadd_rn(tr, kp ? vr : -0.0); ti = __dadd_rn(ti, kp ? vi : -0.0);
+                        }
+                    }
+                    double2 val;
+                    if (x_project(tr, ti, a, val)) {
+                        cur[n] = val;
+                        if (cur_dup) cur_dup[n] = val;
+                        int mir = -1;
+                        if (n >= L + 1 && n < 2 * L + 1) mir = 2 * L - n;
+                        else if (n >= Nreal - 1 && n < Naux) mir = 2 * Naux - n;
+                        if (mir >= 0) {
+                            cur[mir] = make_double2(val.x, -val.y);
+                            if (cur_dup) cur_dup[mir] = make_double2(val.x, -val.y);
+                        }
+                    }
+                }
+                __syncthreads();
+                done = hi;
+            }
+            for (int x = threadIdx.x; x < Np; x += blockDim.x) E0[(long long)m * P + x] = cur[x]; // frame m is final for this sweep
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // post-order walk of numpy's pairwise(a, n) = n <= 128 ? leaf : pairwise(a, n2) + pairwise(a + n2, n - n2),
 // n2 = (n/2) rounded down to a multiple of 8: appends (offset, length, additions after this leaf) triples
@@ -515,6 +625,15 @@ void launch_nofuture_q4(const LwsbView &v, const LwsbW &w, const double *thr, in
     const int *wf = w.wf;
     int nt = (v.Nreal + 2 * v.L) / 2 + 32;
     nt = nt > 512 ? 512 : (nt + 31) / 32 * 32;
+    const int Np = v.Nreal + 2 * v.L;
+    const size_t bytes = (size_t)9 * Np * 16 + (size_t)16 * 6 * 16 + (size_t)2 * (Np + 1) * 8 + 16 * 4 + 16;
+    const char *e = getenv("LWSB_NOFUTURE_RING");
+    if (v.L == 5 && bytes <= 200 * 1024 && !(e && atoi(e) == 0)) { // working set in shared memory
+        auto kern = k_nofuture_q4_ring<5>;
+        if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        kern<<<v.B, nt, bytes, s>>>(v, wr, wi, wf, thr, iters);
+        return;
+    }
     k_nofuture_q4<<<v.B, nt, 0, s>>>(v, wr, wi, wf, thr, iters);
 }
 

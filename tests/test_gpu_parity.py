@@ -347,6 +347,24 @@ def test_online_ring_kernels(gpu, oracle, fs, hop, la, its, n):
         _close(pg.online_lws(As[0][:T]), po.online_lws(As[0][:T]), "online T=%d" % T)
 
 
+def test_nofuture_q4_shared_memory_kernel(gpu, oracle, monkeypatch):
+    """NoFuture_LWSQ4 (the reference's doubled bin offset included) with the frames in a shared-memory window: a ragged batch,
+    several sweeps, against the oracle and against the global-memory kernel (LWSB_NOFUTURE_RING=0)."""
+    for fs, hop, n in ((512, 128, 9000), (64, 16, 3000), (1024, 256, 30000)):
+        po, pg = oracle.lws(fs, hop, mode="music"), gpu.lws(fs, hop, mode="music")
+        As = [np.abs(po.stft(make_signal(k, 5 + i, n + 517 * i))) for i, k in enumerate(("tonal", "white", "tonal"))]
+        for thr in (None, np.zeros(3), np.array([0.7, 0.2])):
+            Ys = pg.nofuture_lws(As, thresholds=thr)
+            for A, Y in zip(As, Ys):
+                _close(Y, po.nofuture_lws(A, thresholds=thr), "nofuture Q4 ring %d/%d" % (fs, hop))
+            monkeypatch.setenv("LWSB_NOFUTURE_RING", "0")
+            Yg = pg.nofuture_lws(As, thresholds=thr)
+            monkeypatch.delenv("LWSB_NOFUTURE_RING")
+            assert all(np.array_equal(a, b) for a, b in zip(Ys, Yg))
+        for T in (1, 2, 4):
+            _close(pg.nofuture_lws(As[0][:T]), po.nofuture_lws(As[0][:T]), "nofuture ring T=%d" % T)
+
+
 _RAIL = lambda lag: pytest.param({"LWSB_ONLINE_RAIL": "1", "LWSB_ONLINE_RAIL_S": lag}, 5, 4, marks=needs_experiments)
 
 
