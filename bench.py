@@ -448,7 +448,8 @@ def run_b200_arm(args):
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
                 "unit": "GB/s", "frac": achieved / peak,
-                "kernel": {"batch": "batch sweep kernel (k_batch_strips)", "online": "online chain kernel (k_online_ring*)",
+                "kernel": {"batch": "batch sweep kernel (k_batch_strips)", "online": "online chain kernel (%s)" % {0: "k_online_generic", 1: "k_online_ring", 2: "k_online_ring2", 3: "k_online_duo",
+                                                                               4: "k_online_flow", 5: "k_online_rail"}.get(ctx.last_online_kernel(), "?"),
                            "nofuture": "no-future sweep kernel"}[dom],
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo_bytes,
                 "algorithmic_bytes_definition": "40 B x bins x row updates asked for, independent of thresholding (SURVEY.md section 8d)",
