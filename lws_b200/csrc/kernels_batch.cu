@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
 #include <type_traits>
@@ -307,17 +308,27 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                 //     oldest frame in flight or two sweeps hits a group three times);
                 //   sweep-fastest: the sweeps of a frame slot padded to groups of 8 lanes, QS frames apart: with an odd
                 //     QS each group covers 8 different residues whatever the slots' frames are -- conflict free.
+                //   rotating (NS = 17 = 16 + 1 only): half-warp h holds sweep slot h and 16 of its 17 frame slots -- all but the one
+                //     that wrapped last (slot ph), whose frame residue doubles its neighbour's; the G left-over tasks share a last
+                //     half-warp.  The lane -> frame slot map changes with ph (a task keeps nothing in registers between macro-steps):
+                //     every full half-warp is conflict free at every macro-step.
                 double f = 0.0; int gfast = 0, lanes_best = 0;
-                for (int order = 0; order < 2; ++order) {
+                for (int order = 0; order < 3; ++order) {
                     const int GP8 = (G + 7) & ~7;
-                    const int lanes = order ? NS * GP8 : NS * G;
+                    const int lanes = order == 1 ? NS * GP8 : NS * G;
                     if (lanes > task_cap) continue;
+                    if (order == 2 && !(NS == 17 && LAGB == 2 && !pair && !duo && !tm)) continue;
+                    if (order == 2 && getenv("LWSB_STRIP_NO_ROTATE")) continue;
                     double cyc = 0.0, ideal = 0.0;
                     for (int ph = 0; ph < NS; ++ph)       // slots 0 .. ph have wrapped to their next frame (+NS)
                         for (int h0 = 0; h0 < lanes; h0 += 16) {
                             int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0, act = 0;
                             for (int l = h0; l < h0 + 16 && l < lanes; ++l) {
-                                const int jj = order ? l / GP8 : l % NS, gg = order ? l % GP8 : l / NS;
+                                int jj = order ? l / GP8 : l % NS, gg = order ? l % GP8 : l / NS;
+                                if (order == 2) {
+                                    if (l < 16 * G) { gg = l / 16; jj = l % 16 < ph ? l % 16 : l % 16 + 1; }
+                                    else { gg = l - 16 * G; jj = ph; }
+                                }
                                 if (gg >= G) continue;
                                 const int fr = jj + (jj <= ph ? NS : 0) - QS * gg;
                                 mx = std::max(mx, ++cnt[((fr % 8) + 8) % 8]); ++act;

@@ -260,6 +260,7 @@ def test_planner_picks_the_measured_best_plans_for_the_baseline_shapes():
     for active in (60, 67, 71, 75, 80, 90, 100):
         pl = _native.debug_plan_strips(513, 4, 5, active, 628, 64)
         assert (pl["cluster"], pl["sweeps_per_pass"], pl["block_bins"], pl["sweep_lag"]) == (2, 7, 8, 4), pl
+        assert pl["frame_slots"] == 17 and pl["sweep_fastest"] == 2, pl  # 16 + 1 frame slots: the rotating lane order
     pl = _native.debug_plan_strips(1025, 8, 5, 150, 5632, 4)
     assert pl["cluster"] == 8 and pl["block_bins"] == 8 and pl["sweep_lag"] >= 8, pl
     assert _native.debug_plan_strips(513, 4, 5, 67, 628, 64, block=4)["block_bins"] == 4
