@@ -57,6 +57,8 @@ enum {
 /* ---- library / context ------------------------------------------------------------- */
 int lwsb_version(void);                      /* 10000*major + 100*minor + patch               */
 int lwsb_has_experiments(void);              /* 1 when built with -DLWSB_EXPERIMENTS (extra kernel variants) */
+int lwsb_strip_launch_mode(void);            /* last launch of the cluster strip kernel in this process: 1 cooperative (co-residency
+                                                guaranteed by the driver), 0 plain, -1 none yet */
 const char *lwsb_last_error(const lwsb_ctx *ctx); /* ctx may be NULL: error of the last failed
                                                 lwsb_create() on this thread                  */
 /* `stream` is a cudaStream_t to launch on (e.g. the caller's current stream) or NULL to let

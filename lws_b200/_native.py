@@ -27,6 +27,7 @@ _ci, _cd, _ll = ctypes.c_int, ctypes.c_double, ctypes.c_longlong
 SIGNATURES = {
     "lwsb_version": (_ci, []),
     "lwsb_has_experiments": (_ci, []),
+    "lwsb_strip_launch_mode": (_ci, []),
     "lwsb_last_error": (ctypes.c_char_p, [_vp]),
     "lwsb_create": (_ci, [_ci, _vp, _vpp]),
     "lwsb_destroy": (_ci, [_vp]),

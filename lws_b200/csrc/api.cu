@@ -336,6 +336,8 @@ int staged_copy(lwsb_ctx *c, char *dev, const std::vector<size_t> &offs, const s
 // ============================================================================ library / context
 extern "C" int lwsb_version(void) { return 200; }
 
+extern "C" int lwsb_strip_launch_mode(void) { return lwsb::strip_launch_mode(); }
+
 extern "C" int lwsb_has_experiments(void)
 {
 #ifdef LWSB_EXPERIMENTS

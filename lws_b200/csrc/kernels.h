@@ -61,5 +61,6 @@ cudaError_t launch_cabs(const double2 *S, double *A, long long n, cudaStream_t s
 cudaError_t launch_sq_norms(const double2 *S, const double2 *R, int B, long long n, double *partial, int nblk, double *out,
                             cudaStream_t s);
 inline int online_generic_max_nreal(int L) { return (1024 - 1) * (L + 1); }
+int strip_launch_mode(); // last strip-kernel launch of the process: 1 cooperative, 0 plain, -1 none
 
 } // namespace lwsb

@@ -188,6 +188,7 @@ __device__ __forceinline__ bool keep_waiting(unsigned &spins, unsigned *status, 
 // The block update, the kernel and its launch code exist twice: 8 bins per block with frames 2 blocks apart (Q = 8, the
 // tensor-memory variant, wide strips) and 4 bins per block with frames 3 blocks apart (12 instead of 16 bins of ring per
 // frame in flight: more tasks fit the shared-memory ring of a narrow strip).
+int g_strip_launch_mode = -1; // last launch: 1 cooperative, 0 plain (launch_strips_t)
 namespace bk8 {
 constexpr int SBK = 8, LAGB = 2;
 constexpr bool HAS_TM = true;
@@ -238,6 +239,8 @@ __global__ void k_debug_fast_math(long long n, unsigned long long seed, unsigned
 
 // Chooses cluster size, strip width and sweeps per pass.  Returns false when the shape is not
 // served by this kernel (the generic kernel takes over).
+int strip_launch_mode() { return g_strip_launch_mode; }
+
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
                  int force_cluster, int max_sweeps, int force_lag, int variant, int fold, int force_block, double avg_iters)
 {
