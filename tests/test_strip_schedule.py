@@ -267,3 +267,28 @@ def test_planner_picks_the_measured_best_plans_for_the_baseline_shapes():
     # a single utterance: several passes in flight on different clusters rather than all sweeps in one pass
     pl = _native.debug_plan_strips(513, 4, 5, 67, 628, 1)
     assert (67 + pl["sweeps_per_pass"] - 1) // pl["sweeps_per_pass"] >= 4, pl
+
+
+def test_rotating_lane_order_covers_every_task_and_is_conflict_free():
+    """The rotating lane order of the strip kernel (strip_body.inc, GFAST == 2; kernels_batch.cu, planner order 2) for strips of
+    16 + 1 frame slots: at every macro-step phase `ph` (slots 0 .. ph have wrapped to their next frame) half-warp h holds sweep
+    slot h with the 16 frame slots other than `ph`, the left-over tasks share the lanes from 16 G on.  The map must hit every
+    (frame slot, sweep slot) exactly once, and the frame residues mod 8 -- the shared-memory bank group of a lane, ring_off --
+    must occur exactly twice in every full half-warp: no bank conflict."""
+    NS, QS = 17, 4
+    for G in range(1, 8):
+        for ph in range(NS):
+            seen = {}
+            for tix in range(17 * G):
+                spill = tix >= 16 * G
+                g = tix - 16 * G if spill else tix >> 4
+                i = tix & 15
+                j = ph if spill else (i if i < ph else i + 1)
+                assert 0 <= j < NS and 0 <= g < G
+                assert (j, g) not in seen
+                seen[(j, g)] = tix
+            assert len(seen) == NS * G
+            for h in range(G):
+                res = [(j + (NS if j <= ph else 0) - QS * h) % 8 for j in range(NS) if j != ph]
+                assert sorted(res) == sorted(list(range(8)) * 2), (G, ph, h, res)
+
