@@ -289,7 +289,8 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
         // pitch) mod 8 cells into its slot, see ring_off in strip_body.inc)
         const int pitch = SBK * NBr + 2 * SL + 7;
         const size_t rowbytes = (size_t)pitch * 16;
-        const size_t fixed = 64 + 16 + (size_t)(iters + 8) * sizeof(int) + 256 + 256; // flags, sweep list, alignment, static shared memory of the kernel
+        // flags, sweep list, alignment, static shared memory of the kernel; Q > 4: the weight table of the bin-loop update
+        const size_t fixed = 64 + 16 + (size_t)(iters + 8) * sizeof(int) + 256 + 256 + (Q > 4 ? (size_t)Q * Q * (SL + 1) * 16 + 16 : 0);
         if (smem_limit < fixed + rowbytes * 8) continue;
         const int Rmax = (int)((smem_limit - fixed) / (rowbytes + 8));
         // resident clusters (cudaOccupancyMaxActiveClusters on B200, one CTA per SM): 148 / 74 / 36-37 / 18
