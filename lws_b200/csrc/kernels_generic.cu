@@ -170,14 +170,31 @@ k_stats(LwsbView v, const double *row_max, double *mean_amp, double *max_amp, co
     const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     if ((threadIdx.x & 31) == 0) sh_m[w] = mx;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double st[64];
-        int sp = 0;
-        for (int l = 0; l < n_leaves; ++l) {
-            st[sp++] = ls[l];
-            for (int a = tab[3 * l + 2]; a > 0; --a) { st[sp - 2] = __dadd_rn(st[sp - 2], st[sp - 1]); --sp; }
+    // the leaf sums are combined in the order of numpy's recursion by ONE thread (a dependent chain); the leaf sums and the
+    // additions-after counts reach it through shared memory in chunks (from global memory the walk cost an L2 round trip per leaf:
+    // 0.3 ms at 2 500 leaves, 6 ms at the 45 000 of a 30 s utterance at 2048 / 256)
+    constexpr int CH = 2048;
+    __shared__ double sh_leaf[CH];
+    __shared__ int sh_adds[CH];
+    __shared__ double sh_st[64];
+    __shared__ int sh_sp;
+    if (threadIdx.x == 0) sh_sp = 0;
+    for (int l0 = 0; l0 < n_leaves; l0 += CH) {
+        const int cnt = min(CH, n_leaves - l0);
+        __syncthreads(); // the leaf sums of this CTA are written (first pass) / the previous chunk is consumed
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) { sh_leaf[i] = ls[l0 + i]; sh_adds[i] = tab[3 * (l0 + i) + 2]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int sp = sh_sp;
+            for (int i = 0; i < cnt; ++i) {
+                sh_st[sp++] = sh_leaf[i];
+                for (int a = sh_adds[i]; a > 0; --a) { sh_st[sp - 2] = __dadd_rn(sh_st[sp - 2], sh_st[sp - 1]); --sp; }
+            }
+            sh_sp = sp;
         }
-        mean_amp[u] = __ddiv_rn(st[0], (double)n); // umr_sum(...) / count  (numpy _methods._mean)
+    }
+    if (threadIdx.x == 0) {
+        mean_amp[u] = __ddiv_rn(sh_st[0], (double)n); // umr_sum(...) / count  (numpy _methods._mean)
         double tm = 0.0;
         for (int i = 0; i < nw; ++i) tm = fmax(tm, sh_m[i]);
         max_amp[u] = tm;
