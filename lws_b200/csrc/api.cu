@@ -689,7 +689,8 @@ static int batch_impl(lwsb_ctx *c, const double *thresholds, int iterations, int
         // run on different clusters at the same time, each a few frames behind the previous one
         std::vector<int> items;
         if (early_out && getenv("LWSB_EARLY_STORE") && atoi(getenv("LWSB_EARLY_STORE")) == 0) early_out = nullptr;
-        const int group = (early_out && c->B >= 32) ? (c->B + 3) / 4 : 0;
+        static const int n_groups = [] { const char *e = getenv("LWSB_EARLY_GROUPS"); return e ? std::max(1, atoi(e)) : 4; }();
+        const int group = (early_out && c->B >= 32) ? (c->B + n_groups - 1) / n_groups : 0;
         const int max_pass = build_work_items(nact.data(), c->B, pl.G, items, group);
         const int n_items = (int)(items.size() / 2);
         c->last_work[0] = c->total_bins * iterations; c->last_work[1] = 0; c->last_work[2] = n_items; c->last_work[3] = max_pass;
