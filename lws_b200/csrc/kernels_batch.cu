@@ -151,6 +151,12 @@ __device__ __forceinline__ void st_release_cluster(unsigned *p, unsigned v)
 {
     asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// release pattern with ONE fence for several flags: fence.acq_rel.cluster, then relaxed stores
+__device__ __forceinline__ void fence_release_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_cluster(unsigned *p, unsigned v)
+{
+    asm volatile("st.relaxed.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ unsigned long long global_ns()
 {
