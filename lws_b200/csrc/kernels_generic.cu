@@ -476,26 +476,29 @@ k_nofuture_q4_ring(LwsbView v, const double *wr, const double *wi, const int *wf
     double2 *E0 = v.E + v.rowbase[u] * (long long)P + (v.c0 - L); // extended (row 0, column 0)
     const double *A0 = v.A + v.rowbase[u] * (long long)P + (v.c0 - L);
     const int lim1 = (Np - L + 1) / 2; // first n whose reads reach the current frame
-    auto fetch_row = [&](int row) { // extended row -> its slot (and the mirror of slot 0), amplitudes -> amp[row & 1]
+    // extended row -> its slot (and the mirror of slot 0); its amplitudes -> amp[row & 1] (not for the ghost rows, which are never
+    // updated: two copies in flight to the same amplitude buffer would not be ordered)
+    auto fetch_row = [&](int row, bool with_amp) {
         const unsigned slot = (unsigned)(row & (NS - 1));
         for (int x = threadIdx.x; x < Np; x += blockDim.x) {
             const double2 *src = E0 + (long long)row * P + x;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(win + slot * Np + x)), "l"(src) : "memory");
             if (slot == 0)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(win + NS * Np + x)), "l"(src) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(amp + (row & 1) * (Np + 1) + x)),
-                         "l"(A0 + (long long)row * P + x) : "memory");
+            if (with_amp)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(amp + (row & 1) * (Np + 1) + x)),
+                             "l"(A0 + (long long)row * P + x) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     for (int it = 0; it < iters; ++it) {
         const double thr = __dmul_rn(thresholds[it], mean); // lws.pyx:298
         __syncthreads();
-        for (int row = 0; row < Q; ++row) fetch_row(row); // the ghost rows 0 .. Q-2 and the first frame
+        for (int row = 0; row < Q; ++row) fetch_row(row, row == Q - 1); // the ghost rows 0 .. Q-2 and the first frame
         for (int m = Q - 1; m < T + Q - 1; ++m) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads(); // row m and its amplitudes are in; everybody is done with frame m-1
-            if (m + 1 < T + Q - 1) fetch_row(m + 1); // into the slot of row m-7
+            if (m + 1 < T + Q - 1) fetch_row(m + 1, true); // into the slot of row m-7
             const double *arow = amp + (m & 1) * (Np + 1);
             double2 *cur = win + (m & (NS - 1)) * Np, *cur_dup = (m & (NS - 1)) == 0 ? win + NS * Np : nullptr;
             int done = L;
