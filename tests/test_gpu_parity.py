@@ -570,6 +570,32 @@ def test_cfg5_plan_vs_oracle(gpu, oracle):
     _close(Ys[2], po.batch_lws(As[2], thresholds=thr), "cfg5 plan, white utterance")
 
 
+@pytest.mark.parametrize("fs,hop,n_sig,n_utt,its,cluster", [(2048, 512, 24000, 8, 30, 4), (1024, 512, 30000, 4, 24, 2), (4096, 1024, 50000, 1, 12, 8),
+                                                          (1024, 256, 12000, 5, 16, 2)])
+def test_rotating_lane_order_vs_oracle(gpu, oracle, monkeypatch, fs, hop, n_sig, n_utt, its, cluster):
+    """Strips of 16 + 1 frame slots run the rotating lane order (lane -> frame slot changes with the macro-step): other spectra
+    and cluster sizes than BASELINE configs[1], ragged batches, several passes -- against the oracle and against the
+    frame-fastest order (LWSB_STRIP_NO_ROTATE)."""
+    from lws_b200 import api
+    ctx = api._context(0)
+    po, pg = oracle.lws(fs, hop), gpu.lws(fs, hop)
+    As = [np.abs(po.stft(make_signal("tonal" if i % 2 else "white", 700 + i, n_sig + 1500 * i))) for i in range(n_utt)]
+    thr = gpu.get_thresholds(its, 1.5, 0.2, 1)
+    try:
+        ctx.set_tuning(0, cluster, 0)
+        Ys = pg.batch_lws(As, thresholds=thr)
+        plan = ctx.last_batch_plan()
+        assert plan is not None and plan["frame_slots"] == 17 and plan["sweep_fastest"] == 2, plan
+        monkeypatch.setenv("LWSB_STRIP_NO_ROTATE", "1")
+        Yf = pg.batch_lws(As, thresholds=thr)
+        assert ctx.last_batch_plan()["sweep_fastest"] != 2
+    finally:
+        ctx.set_tuning(0, 0, 0)
+    assert all(np.array_equal(a, b) for a, b in zip(Ys, Yf))
+    for A, Y in zip(As[:2], Ys[:2]):
+        _close(Y, po.batch_lws(A, thresholds=thr), "rotating lane order %s" % (plan,))
+
+
 def test_generic_and_strip_kernels_agree(gpu):
     from lws_b200 import _native
     p = gpu.lws(1024, 256)
