@@ -304,15 +304,18 @@ def test_full_size_properties(gpu):
     assert c1 > c0 + 5.0, (c0, c1)
 
 
-def test_strip_kernel_is_launched_cooperatively(gpu):
-    """The clusters of a strip-kernel launch wait for one another: the launch is cooperative, i.e. the driver guarantees that all of
-    them are resident (or refuses the launch) also when other work shares the GPU; LWSB_STRIP_COOP=0 is the plain launch."""
+def test_strip_kernel_cooperative_launch(gpu, monkeypatch):
+    """The clusters of a strip-kernel launch wait for one another.  LWSB_STRIP_COOP=1 makes the launch cooperative: the driver
+    guarantees that all of them are resident (or refuses the launch) also when other work shares the GPU.  The default is the
+    plain launch with the grid sized by the occupancy query (Nsight Compute cannot replay cooperative cluster launches)."""
     from lws_b200 import _native
     p = gpu.lws(512, 128, batch_iterations=6, batch_alpha=1)
     A = np.abs(p.stft(make_signal("white", 8, 9000)))
     Y = p.batch_lws(A)
-    assert _native.lib().lwsb_strip_launch_mode() == 1
+    assert _native.lib().lwsb_strip_launch_mode() == 0
+    monkeypatch.setenv("LWSB_STRIP_COOP", "1")
     assert np.array_equal(p.batch_lws([A, A[:40]])[0], Y)
+    assert _native.lib().lwsb_strip_launch_mode() == 1
 
 
 def test_cfg2_one_utterance_vs_oracle(gpu, oracle):
