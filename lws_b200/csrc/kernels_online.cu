@@ -1,14 +1,17 @@
-// kernels_online.cu -- online_lws (TF-RTISI-LA, lwslib.cpp:1424-1492) with the working set in shared memory
-// and the update rule resolved at compile time.
+// kernels_online.cu -- online_lws (TF-RTISI-LA, lwslib.cpp:1424-1492) with the working set in shared memory.
 //
-// The whole schedule is one chain of row updates (lwsb_common.h: lwsb_online_decode); row update j runs S bins
-// behind row update j-1, S = the smallest multiple of Q that is >= L+1, so that at any step every thread of the
-// CTA is on a bin of the SAME residue p = bin mod Q: the per-residue weights then come out of the kernel
-// parameter bank with compile-time indices and one `switch (p)` selects the code for the step.  The ~Nreal/S
-// row updates in flight touch only the extended rows [m_lo - LA, m_hi + 2(Q-1)]; a ring of R rows (R a power
-// of two, sized on the host from the exact maximum of the schedule) keeps them in shared memory, rows are
-// copied in when the front of the chain first needs them and written back when the tail has passed.
-// One CTA per utterance.  Arithmetic: the reference's, operation for operation (exact.cuh).
+// The whole schedule is one chain of row updates (lwsb_common.h: lwsb_online_decode); row update j runs S bins behind row
+// update j-1.  The ~Nreal/S row updates in flight touch only the extended rows [m_lo - LA, m_hi + 2(Q-1)]; a ring of R rows (R a
+// power of two, sized on the host from the exact maximum of the schedule) keeps them in shared memory, rows are copied in when
+// the front of the chain first needs them and written back when the tail has passed.  One CTA per utterance.  Arithmetic: the
+// reference's, operation for operation (exact.cuh).  Kernels, in the order launch_online_ring tries them:
+//   k_online_flow  (Q <= 4, shipping)  K = 4 warps per row update taking turns, so that only the order-bound chain of a bin is on
+//                                      the critical path; per-lane data instead of per-residue code; S = K + L = 9
+//   k_online_duo   (Q <= 4)            two bins per step on two lanes (spectra too wide for four warps per row update)
+//   k_online_ring2 / k_online_ring     two bins / one bin per step in one lane; S a multiple of Q so that every thread of a step is on
+//                                      the same residue and the per-residue weights come from the parameter bank (Q = 8)
+//   k_online_rail  (experiments build) value warps + chain warps
+// (k_online_generic in kernels_generic.cu serves every other shape from global memory.)
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdlib>
