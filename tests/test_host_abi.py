@@ -272,6 +272,83 @@ def test_online_chain_two_bins_per_step(oracle, name, LA):
     assert relF(got, want) < 1e-12
 
 
+def _flow_replay(p, po, A0, LA, iters, S, K):
+    """k_online_flow's schedule: row update j is on bin b - S j at bin-step b; K warps per row update take the bin-steps in turn.  A
+    warp forms the term values of the other frames for bin-step b any time after its own hand-over of bin-step b - K: modelled as
+    "every such cell was last written at bin-step <= b - K" (then reading it at any moment of the window gives the same value);
+    the centre-frame terms are read after the hand-over of b - 1.  No cell read at b may be written at b by another row update."""
+    Q, L = p.W.shape[1], p.W.shape[2] - 1
+    T, Nreal = A0.shape
+    thr = lws_b200.get_thresholds(iters, 1, 0.1, 1)
+    mean = np.mean(A0)
+    E = dsp.extspec(A0.astype(np.complex128), L, Q)
+    A = np.abs(E)
+    fold = FOLD.get(Q, 0)
+    tabs = {("W", rf): _tables(p.W, fold, rf, 1) for rf in range(2, Q + 1)}
+    tabs["ai"] = _tables(p.W_ai, fold, 1, 0)
+    tabs["af"] = _tables(p.W_af, fold, 1, 1)
+    chain = _native.debug_online_chain(T, iters, LA, Q)
+    last = np.full(E.shape, -10 ** 9, dtype=np.int64)   # bin-step of the last write of a cell
+    for b in range(S * (len(chain) - 1) + Nreal):
+        snap = E.copy()
+        written, reads = {}, []
+        for j in range(max(0, (b - Nreal) // S), min(len(chain) - 1, b // S) + 1):
+            c = b - S * j
+            if not (0 <= c < Nreal):
+                continue
+            row, which, rframe, cframe, ti = chain[j]
+            terms = tabs[("W", rframe)] if which == 0 else (tabs["ai"] if which == 1 else tabs["af"])
+            a = A[row, c + L]
+            if not (a > (0.0 if ti < 0 else thr[ti] * mean)):
+                continue
+            dr, dk, co = terms[c % len(terms)]
+            for q in range(len(co)):
+                key = (row + dr[q], c + L + dk[q])
+                reads.append(key + (j,))
+                if dr[q] != 0 and last[key] > b - K:
+                    return None, "row update %d, bin %d reads cell %s written at bin-step %d > %d - %d" % (j, c, key, last[key], b, K)
+            tsum = np.sum(co * snap[row + dr, c + L + dk])
+            if abs(tsum) > 0:
+                v = tsum * a / abs(tsum)
+                tg = [((row, c + L), v)]
+                if 1 <= c <= L:
+                    tg.append(((row, L - c), np.conj(v)))
+                elif Nreal - 1 - L <= c <= Nreal - 2:
+                    tg.append(((row, L + 2 * (Nreal - 1) - c), np.conj(v)))
+                for key, val in tg:
+                    E[key] = val
+                    written[key] = j
+        for (r_, c_, j) in reads:
+            if written.get((r_, c_), j) != j:
+                return None, "cell (%d, %d) read by row update %d and written by %d in bin-step %d" % (r_, c_, j, written[(r_, c_)], b)
+        for key in written:
+            last[key] = b
+    return E[Q - 1:Q - 1 + T, L:L + Nreal], None
+
+
+@pytest.mark.parametrize("name,LA", [("q4", 3), ("q2_la4", 4), ("q4_la0", 0), ("q4_la5", 5), ("q4_la1", 1)])
+def test_online_flow_schedule(oracle, name, LA):
+    """k_online_flow: lag S = K + L between row updates is sufficient for K warps per row update taking turns (K = 2, 3, 4), and
+    S = K + L - 1 is not (the replay finds a cell read inside the window in which it is written)."""
+    case = [c for c in SMALL_CASES if c["name"] == name][0]
+    p = lws_b200.lws(*case["args"], **case["kwargs"])
+    po = oracle.lws(*case["args"], **case["kwargs"])
+    assert p.look_ahead == LA
+    L = p.W.shape[2] - 1
+    A0 = np.abs(golden(name)["X"])[:9]
+    iters = 2
+    want = po.online_lws(A0, thresholds=lws_b200.get_thresholds(iters, 1, 0.1, 1))
+    for K in (2, 3, 4):
+        got, err = _flow_replay(p, po, A0, LA, iters, K + L, K)
+        assert err is None, (K, err)
+        assert relF(got, want) < 1e-12
+        got, err = _flow_replay(p, po, A0, LA, iters, K + L + 2, K)
+        assert err is None and relF(got, want) < 1e-12
+    _, err = _flow_replay(p, po, A0, LA, iters, 4 + L - 1, 4)
+    assert err is not None
+
+
+
 def test_nofuture_q4_table_reproduces_reference_indexing(oracle):
     """LWSB_FOLD_NF4 terms applied with the reference's flat offset (m+dr)*Np + 2e + dk, raster order."""
     p, po = lws_b200.lws(32, 8), oracle.lws(32, 8)
