@@ -83,6 +83,8 @@ struct StripParams {
     const double *max_amp;     // [B]
     int iters;
     int C, NBr, NBV, NS, G, R, pitch, QS, GFAST;
+    int poll_sleep; // LWSB_STRIP_POLL_SLEEP=1: the neighbour-flag polls back off with __nanosleep(32) (default: tight spin, the compute
+                    // warps of the CTA are waiting for the control warp anyway: 0.5 ms of 98 at BASELINE configs[1])
     unsigned *status;          // [0]: 0 ok, else first watchdog code
     // work list: one item per (utterance, pass), pass-major; cluster k takes items k, k + #clusters, ...  A pass reads
     // each frame after the previous pass of the same utterance -- possibly running on another cluster at the
@@ -414,6 +416,7 @@ cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const 
     prm.items = reinterpret_cast<const int2 *>(items); prm.n_items = n_items; prm.max_pass = max_pass; prm.done = done; prm.trace = trace;
     prm.v = v; prm.thr = thr; prm.max_amp = max_amp; prm.iters = iters;
     prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch; prm.QS = pl.QS; prm.GFAST = pl.GFAST;
+    { const char *e = getenv("LWSB_STRIP_POLL_SLEEP"); prm.poll_sleep = e ? atoi(e) : 0; }
     prm.status = status;
     if (pl.SBK == 4) {
 #ifdef LWSB_EXPERIMENTS
