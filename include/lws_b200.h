@@ -225,7 +225,7 @@ int lwsb_get_stats(lwsb_ctx *ctx, double *mean_amp, double *max_amp);
  *    into (row, weight set, rframe, cframe, threshold index or -1). */
 int lwsb_debug_terms(const double *wr, const double *wi, int Q, int L, int fold, int rframe, int cframe, int p,
                      int max_terms, int *dr, int *dk, double *cr, double *ci);
-/*  - lwsb_debug_plan_strips: the plan the cluster strip kernel would use (same 13 numbers as
+/*  - lwsb_debug_plan_strips: the plan the cluster strip kernel would use (same 15 numbers as
  *    lwsb_last_batch_plan) for a shape and a shared-memory / SM budget; returns 0 when the generic kernel serves it. */
 int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, int maxT, int B, long long smem_limit,
                            int sm_count, int force_cluster, int max_sweeps, int force_block, int *out9);

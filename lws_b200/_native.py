@@ -445,7 +445,8 @@ def debug_terms(Wc, fold, rframe, cframe, p):
 
 
 PLAN_KEYS = ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots", "sweeps_per_pass", "ring_rows",
-             "ring_pitch", "threads", "smem_bytes", "sweep_lag", "sweep_fastest", "tensor_memory", "block_bins")
+             "ring_pitch", "threads", "smem_bytes", "sweep_lag", "sweep_fastest", "tensor_memory", "block_bins", "sweep_extra_from",
+             "load_lead")
 
 
 def debug_work_items(active_sweeps, sweeps_per_pass):

@@ -1435,8 +1435,8 @@ extern "C" int lwsb_last_batch_plan(const lwsb_ctx *c, int *out9)
     if (!c || !out9) return LWSB_ERR_ARG;
     if (c->last_kernel != 1) return 0;
     const StripPlan &p = c->last_plan;
-    const int v[13] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM, p.SBK};
-    for (int i = 0; i < 13; ++i) out9[i] = v[i];
+    const int v[15] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM, p.SBK, p.GX, p.LEAD};
+    for (int i = 0; i < 15; ++i) out9[i] = v[i];
     return 1;
 }
 
@@ -1489,8 +1489,8 @@ extern "C" int lwsb_debug_plan_strips(int Nreal, int Q, int L, int iterations, i
     if (!out9) return LWSB_ERR_ARG;
     StripPlan p;
     if (!plan_strips(Nreal, Q, L, iterations, maxT, B, (size_t)smem_limit, sm_count, &p, force_cluster, max_sweeps, 0, 0, 0, force_block)) return 0;
-    const int v[13] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM, p.SBK};
-    for (int i = 0; i < 13; ++i) out9[i] = v[i];
+    const int v[15] = {p.C, p.NBr, p.NBV, p.NS, p.G, p.R, p.pitch, p.nthreads, p.smem_bytes, p.QS, p.GFAST, p.TM, p.SBK, p.GX, p.LEAD};
+    for (int i = 0; i < 15; ++i) out9[i] = v[i];
     return 1;
 }
 

@@ -39,6 +39,8 @@ struct StripPlan {
     int smem_limit; // shared-memory budget the plan was made for
     int SBK, LAGB;  // bins per block (8 or 4) and blocks between consecutive frames (2 or 3)
     int C, NBr, NBV, NS, G, R, pitch, nthreads, smem_bytes, QS, GFAST, TM; // TM: 0 one thread per task, LWSB_VARIANT_TM, LWSB_VARIANT_PAIR + window mode
+    int GX;   // sweep slots g >= GX run one more frame behind (sweep offset QS g + 1); GX == G: none
+    int LEAD; // frames of TMA look-ahead (2; 1 when the extra frame of GX takes its ring row)
 };
 bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t smem_limit, int sm_count, StripPlan *out,
                  int force_cluster = 0, int max_sweeps = 0, int force_lag = 0, int variant = 0, int fold = 0, int force_block = 0,

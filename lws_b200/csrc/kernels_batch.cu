@@ -82,7 +82,7 @@ struct StripParams {
     const double *thr;         // [iters] unscaled thresholds
     const double *max_amp;     // [B]
     int iters;
-    int C, NBr, NBV, NS, G, R, pitch, QS, GFAST;
+    int C, NBr, NBV, NS, G, R, pitch, QS, GFAST, GX, LEAD;
     int poll_sleep; // LWSB_STRIP_POLL_SLEEP=1: the neighbour-flag polls back off with __nanosleep(32) (default: tight spin, the compute
                     // warps of the CTA are waiting for the control warp anyway: 0.5 ms of 98 at BASELINE configs[1])
     unsigned *status;          // [0]: 0 ok, else first watchdog code
@@ -324,31 +324,37 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                 //     that wrapped last (slot ph), whose frame residue doubles its neighbour's; the G left-over tasks share a last
                 //     half-warp.  The lane -> frame slot map changes with ph (a task keeps nothing in registers between macro-steps):
                 //     every full half-warp is conflict free at every macro-step.
-                double f = 0.0; int gfast = 0, lanes_best = 0;
-                for (int order = 0; order < 3; ++order) {
+                // Rotating order with an even lag: the G left-over tasks (one per sweep slot, frame slot ph) have frame residues
+                // ph + 1 - QS g, i.e. only two classes for QS = 4: a 4-way conflict in their half-warp.  One extra frame of lag from
+                // sweep slot GX = (G + 1) / 2 on spreads them over four classes (2-way); its ring row is taken from the TMA look-ahead
+                // (1 frame instead of 2: a frame clock is two macro-steps, ~17 us, a row load ~1 us).  LWSB_STRIP_NO_EXTRA disables.
+                double f = 0.0; int gfast = 0, lanes_best = 0, gx_best = G;
+                for (int order = 0; order < 4; ++order) { // order 3: rotating with the extra frame of lag
+                    const int gx = order == 3 ? (G + 1) / 2 : G;
+                    if (order == 3 && (G < 3 || (QS & 1) || getenv("LWSB_STRIP_NO_EXTRA"))) continue;
                     const int GP8 = (G + 7) & ~7;
                     const int lanes = order == 1 ? NS * GP8 : NS * G;
                     if (lanes > task_cap) continue;
-                    if (order == 2 && !(NS == 17 && LAGB == 2 && !pair && !duo && !tm)) continue;
-                    if (order == 2 && getenv("LWSB_STRIP_NO_ROTATE")) continue;
+                    if (order >= 2 && !(NS == 17 && LAGB == 2 && !pair && !duo && !tm)) continue;
+                    if (order >= 2 && getenv("LWSB_STRIP_NO_ROTATE")) continue;
                     double cyc = 0.0, ideal = 0.0;
                     for (int ph = 0; ph < NS; ++ph)       // slots 0 .. ph have wrapped to their next frame (+NS)
                         for (int h0 = 0; h0 < lanes; h0 += 16) {
                             int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0, act = 0;
                             for (int l = h0; l < h0 + 16 && l < lanes; ++l) {
                                 int jj = order ? l / GP8 : l % NS, gg = order ? l % GP8 : l / NS;
-                                if (order == 2) {
+                                if (order >= 2) {
                                     if (l < 16 * G) { gg = l / 16; jj = l % 16 < ph ? l % 16 : l % 16 + 1; }
                                     else { gg = l - 16 * G; jj = ph; }
                                 }
                                 if (gg >= G) continue;
-                                const int fr = jj + (jj <= ph ? NS : 0) - QS * gg;
+                                const int fr = jj + (jj <= ph ? NS : 0) - QS * gg - (gg >= gx ? 1 : 0);
                                 mx = std::max(mx, ++cnt[((fr % 8) + 8) % 8]); ++act;
                             }
                             cyc += mx; ideal += (act + 7) / 8;
                         }
                     const double ff = ideal > 0.0 ? cyc / ideal : 1.0;
-                    if (lanes_best == 0 || ff < f) { f = ff; gfast = order; lanes_best = lanes; }
+                    if (lanes_best == 0 || ff < f) { f = ff; gfast = order == 3 ? 2 : order; lanes_best = lanes; gx_best = gx; }
                 }
                 if (lanes_best == 0) continue;
                 if (force_lag > 0 && QS != force_lag) continue;
@@ -389,7 +395,8 @@ bool plan_strips(int Nreal, int Q, int L, int iters, int maxT, int B, size_t sme
                     out->SBK = SBK; out->LAGB = LAGB;
                     out->C = C; out->NBr = NBr; out->NBV = NBV; out->NS = NS; out->G = G; out->pitch = pitch; out->QS = QS; out->GFAST = gfast;
                     out->TM = tm ? LWSB_VARIANT_TM : (pair ? var : (duo ? LWSB_VARIANT_DUO : 0));
-                    out->R = QS * (G - 1) + 2 * Q + SLEAD + NS;
+                    out->GX = gx_best; out->LEAD = gx_best < G ? SLEAD - 1 : SLEAD;
+                    out->R = QS * (G - 1) + (gx_best < G ? 1 : 0) + 2 * Q + out->LEAD + NS; // the extra frame takes the row the shorter look-ahead frees
                     out->nthreads = duo ? 2 * ((lanes_best + 31) / 32 * 32) : ((pair ? 2 : 1) * lanes_best + 31) / 32 * 32 + 32;
                     out->smem_bytes = (int)(fixed + (size_t)out->R * (rowbytes + 8));
                     out->smem_limit = (int)smem_limit;
@@ -415,7 +422,7 @@ cudaError_t launch_batch_strips(const LwsbView &v, const double *wr_host, const 
     StripParams prm;
     prm.items = reinterpret_cast<const int2 *>(items); prm.n_items = n_items; prm.max_pass = max_pass; prm.done = done; prm.trace = trace;
     prm.v = v; prm.thr = thr; prm.max_amp = max_amp; prm.iters = iters;
-    prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch; prm.QS = pl.QS; prm.GFAST = pl.GFAST;
+    prm.C = pl.C; prm.NBr = pl.NBr; prm.NBV = pl.NBV; prm.NS = pl.NS; prm.G = pl.G; prm.R = pl.R; prm.pitch = pl.pitch; prm.QS = pl.QS; prm.GFAST = pl.GFAST; prm.GX = pl.GX; prm.LEAD = pl.LEAD;
     { const char *e = getenv("LWSB_STRIP_POLL_SLEEP"); prm.poll_sleep = e ? atoi(e) : 0; }
     prm.status = status;
     if (pl.SBK == 4) {

@@ -42,6 +42,8 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
     C, NBr, NBV, NS, G, R = (plan[k] for k in ("cluster", "blocks_per_strip", "virtual_blocks", "frame_slots",
                                                 "sweeps_per_pass", "ring_rows"))
     QS = plan["sweep_lag"]
+    GX, LEAD = plan["sweep_extra_from"], plan["load_lead"]   # sweep slots >= GX run one more frame behind; frames of load look-ahead
+    off = lambda g: QS * g + (1 if g >= GX else 0)
     SBK = plan["block_bins"]
     LAGB = (SBK + SL + SBK - 1) // SBK   # blocks between consecutive frames: LAGB * SBK >= SBK + L
     assert QS >= Q and NBV % LAGB == 0 and NS * LAGB == NBV
@@ -49,10 +51,10 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
     amax = A[Q - 1:Q - 1 + T, SL:SL + Nreal].max()
     act = [i for i, th in enumerate(thr_list) if th * mean < amax]
     npass = (len(act) + G - 1) // G
-    assert R >= QS * (G - 1) + 2 * Q + SLEAD + NS
+    assert R >= off(G - 1) + 2 * Q + LEAD + NS and LEAD >= 1 and (GX == G or LEAD == SLEAD - 1)
     for ps in range(npass):
         Gp = min(G, len(act) - ps * G)
-        nsteps = LAGB * (T - 1 + QS * (Gp - 1)) + NBV
+        nsteps = LAGB * (T - 1 + off(Gp - 1)) + NBV
         strips = [Strip(c, plan, Nreal) for c in range(C)]
 
         def load(st, e):
@@ -63,7 +65,7 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
             st.tag[e % R] = e
 
         for st in strips:
-            for e in range(min(Tp, 2 * (Q - 1) + SLEAD + 1)):
+            for e in range(min(Tp, 2 * (Q - 1) + LEAD + 1)):
                 load(st, e)
         for wall in range(nsteps + (C - 1) * NBr):
             snaps = [st.ring.copy() for st in strips]
@@ -78,7 +80,7 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
                         d = t - LAGB * j
                         if d < 0:
                             continue
-                        xb, m = d % NBV, j + NS * (d // NBV) - QS * g
+                        xb, m = d % NBV, j + NS * (d // NBV) - off(g)
                         if not (xb < st.nb_my and 0 <= m < T):
                             continue
                         me = (st.c, g, j)
@@ -133,7 +135,7 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
                     continue
                 tf = t - (st.nb_my - 1)
                 if st.nb_my > 0 and tf >= 0 and tf % LAGB == 0:
-                    m = tf // LAGB - QS * (Gp - 1)
+                    m = tf // LAGB - off(Gp - 1)
                     if 0 <= m < T:
                         e = m + Q - 1
                         assert st.tag[e % R] == e
@@ -141,7 +143,7 @@ def replay(E, A, terms, thr_list, mean, Q, T, Nreal, plan):
                         hi = SL + (Nreal - st.b0) + SL if st.c == C - 1 else SL + SBK * NBr
                         E[e, st.b0 + lo:st.b0 + hi] = st.ring[e % R, lo:hi]
                 if (t + 1) % LAGB == 0:
-                    e = (t + 1) // LAGB + 2 * (Q - 1) + SLEAD
+                    e = (t + 1) // LAGB + 2 * (Q - 1) + LEAD
                     if e < Tp:
                         load(st, e)
     return E
@@ -157,6 +159,8 @@ CASES = [  # (golden case, frames, thresholds, smem budget, cluster, sweeps per 
     ("cfg1_short", 10, [0.8, 0.3, 0.2, 0.25, 0.1, 0.3], 232448, 4, 2),  # 257 bins on 4 strips (9 blocks each, 6 in the last)
     ("rand513", 5, [0.8, 0.3], 232448, 8, 0),                      # 513 bins on 8 strips of 9 blocks (virtual 10)
     ("cfg1_short", 6, [0.8, 0.3, 0.5], 60000, 2, 0),               # a tight ring: small G forced by the budget
+    ("rand513", 6, [0.8, 0.3, 0.2, 0.5, 0.1, 0.3, 0.2, 0.4, 0.1], 232448, 2, 7),  # BASELINE configs[1]'s plan: 17 frame slots, 7 sweeps per pass,
+                                                                                     # one extra frame of lag from sweep slot 4 on, two passes
     # 4-bin blocks, frames 3 blocks apart; the L = 5 halo bins span two blocks
     ("q4", 20, [0.5, 0.2, 0.3, 0.1, 0.05], 232448, 0, 0, 4),
     ("q4", 9, [0.5, 0.2, 0.3, 0.1, 0.05], 232448, 0, 2, 4),
@@ -229,7 +233,9 @@ def test_planner_properties():
                         assert NBV % LAGB == 0 and NBV >= NBr and NS * LAGB == NBV and NBr >= 2 and SBK * NBr >= 2 * SL
                         assert C * NBr * SBK >= Nreal                          # the strips cover every bin
                         assert (C - 1) * NBr * SBK <= Nreal - 1 - SL           # mirror zone inside the last strip
-                        assert R >= pl["sweep_lag"] * (G - 1) + 2 * Q + SLEAD + NS and 1 <= G <= iters and pl["sweep_lag"] >= Q
+                        extra = 1 if pl["sweep_extra_from"] < G else 0
+                        assert R >= pl["sweep_lag"] * (G - 1) + extra + 2 * Q + pl["load_lead"] + NS and 1 <= G <= iters and pl["sweep_lag"] >= Q
+                        assert pl["load_lead"] == SLEAD - extra
                         assert pl["ring_pitch"] % 2 == 1 and pl["ring_pitch"] >= SBK * NBr + 2 * SL
                         assert pl["smem_bytes"] <= smem and pl["threads"] <= 256 and pl["threads"] >= NS * G + 32 and (not pl["tensor_memory"] or NS * G <= 128)
                         assert R * pl["ring_pitch"] * 16 + R * 8 + 32 + 4 * iters <= pl["smem_bytes"]
