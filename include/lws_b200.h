@@ -182,11 +182,15 @@ int lwsb_last_stage_ms(lwsb_ctx *ctx, float *ms3);
  * that can move a bin (threshold below max|S|; the others are dropped before launch), work items, passes} */
 int lwsb_last_batch_work(const lwsb_ctx *ctx, long long *out4);
 /* which kernel the last lwsb_online call ran: 0 generic (global memory), 1 shared-memory ring with one bin per step,
- * 2 ring with two bins per step and thread, 3 ring with two bins per step on two lanes (env LWSB_ONLINE_DUO=0 selects 2) */
+ * 2 ring with two bins per step and thread, 3 ring with two bins per step on two lanes (env LWSB_ONLINE_DUO=0 selects 2),
+ * 4 ring with four warps per row update taking turns (the default for Q <= 4; LWSB_ONLINE_FLOW=0 selects 3),
+ * 5 value warps + chain warps (experiments build) */
 int lwsb_last_online_kernel(const lwsb_ctx *ctx);
 /* 1 and the plan {cluster size, blocks per strip, virtual blocks, frame slots, sweeps per pass, ring rows,
- * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order, kernel variant, bins per block} (13 ints) when the last lwsb_batch ran the cluster strip kernel, 0 when it
- * ran the generic wavefront kernel */
+ * ring pitch, threads, shared-memory bytes, frames between sweeps, thread order (0 frame slots fastest, 1 sweep slots
+ * fastest, 2 rotating), kernel variant, bins per block, first sweep slot that runs one more frame behind (= sweeps per
+ * pass: none), frames of TMA look-ahead} (15 ints; pass room for 16) when the last lwsb_batch ran the cluster strip
+ * kernel, 0 when it ran the generic wavefront kernel */
 int lwsb_last_batch_plan(const lwsb_ctx *ctx, int *out9);
 /* tuning knobs of the strip kernel's planner (0 = automatic): shared-memory budget per CTA in bytes, cluster
  * size (1, 2, 4, 8) and sweeps in flight per pass.  Also settable through the environment variables
