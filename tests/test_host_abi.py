@@ -396,3 +396,88 @@ def test_native_create_weights_is_parity_grade_for_batch_sweeps(oracle):
         thr = oracle.get_thresholds(100, 100, 0.1, 1)
         Y0, Y1 = oracle.batch_lws(A, po.W, thr), oracle.batch_lws(A, Wn, thr)
         assert np.linalg.norm(Y1 - Y0) / np.linalg.norm(Y0) < 1e-10
+
+
+def _frame_base(m, it, LA):
+    """lwsb_online_frame_base (lwsb_common.h): number of row updates before frame m"""
+    if LA <= 0:
+        return m * (1 + it)
+    if m <= LA:
+        return m + it * m * (m + 1) // 2
+    return LA + it * LA * (LA + 1) // 2 + (m - LA) * (1 + it * (LA + 1))
+
+
+def _frame_of(it, LA, j):
+    m = 0
+    while _frame_base(m + 1, it, LA) <= j:
+        m += 1
+    return m
+
+
+@pytest.mark.parametrize("T,Nreal,iters,LA,Q", [(9, 33, 2, 3, 4), (1, 17, 3, 3, 4), (30, 129, 1, 0, 2), (12, 257, 2, 5, 4), (3, 513, 4, 1, 4),
+                                                 (40, 65, 1, 2, 2)])
+def test_online_flow_barrier_protocol_terminates(T, Nreal, iters, LA, Q):
+    """The control flow of k_online_flow as a discrete simulation: K warps per group of 32 row updates, hand-over barriers 1 + b mod K
+    shared by the warps that committed bin-step b and the warps about to run b + 1, CTA barriers around the ring residency changes
+    (with the role of bin-step bs taking its hand-over BEFORE the drain).  Every warp must reach the end, every barrier must be
+    met by exactly the warps it is sized for, for any shape -- no dead-lock, no stray arrival."""
+    K, L = 4, 5
+    S = K + L
+    n = _frame_base(T, iters, LA)
+    assert n == len(_native.debug_online_chain(T, iters, LA, Q))
+    tasks = (Nreal + S - 1) // S + 1
+    G = (tasks + 31) // 32
+    bend = S * (n - 1) + (Nreal - 1) + 1
+    Tp = T + 2 * (Q - 1)
+
+    def warp(role, grp):
+        hi, ev_j = -1, 0
+        b, bmod, jhi = role, role, 0
+        while b <= bend:
+            waited = False
+            if bmod < K and jhi >= ev_j:
+                jh = min(jhi, n - 1)
+                mfront = _frame_of(iters, LA, jh)
+                ev_j = _frame_base(mfront + 1, iters, LA) if mfront + 1 < T else 1 << 62
+                need_hi = min(Tp - 1, mfront + 2 * (Q - 1))
+                if need_hi > hi:
+                    if bmod == 0 and b > 0:
+                        yield ("bar", 1 + (role + K - 1) % K); waited = True
+                    yield ("cta",); yield ("cta",); yield ("cta",)
+                    hi = need_hi
+            if b > 0 and not waited:
+                yield ("bar", 1 + (role + K - 1) % K)
+            if b < bend:
+                yield ("bar", 1 + role)
+            if b + K > bend:
+                break
+            b += K; bmod += K
+            if bmod >= S:
+                bmod -= S; jhi += 1
+        yield ("cta",)
+
+    warps = {(r, g): warp(r, g) for r in range(K) for g in range(G)}
+    waiting = {}
+    for key, w in warps.items():
+        waiting[key] = next(w, None)
+    steps = 0
+    while any(v is not None for v in waiting.values()):
+        steps += 1
+        progressed = False
+        live = [k for k, v in waiting.items() if v is not None]
+        if all(waiting[k] == ("cta",) for k in live) and len(live) == K * G:
+            for k in live:
+                waiting[k] = next(warps[k], None)
+            progressed = True
+        else:
+            for bid in range(1, K + 1):
+                at = [k for k in live if waiting[k] == ("bar", bid)]
+                assert len(at) <= 2 * G, "barrier %d oversubscribed: %s" % (bid, at)
+                if len(at) == 2 * G:
+                    assert sorted(set(r for r, _ in at)) == sorted({(bid - 1) % K, bid % K}), at  # committers of b and waiters of b + 1
+                    for k in at:
+                        waiting[k] = next(warps[k], None)
+                    progressed = True
+        assert progressed, "dead-lock: %s" % {k: v for k, v in waiting.items() if v is not None}
+        assert steps < 10 * (bend + 10) * K
+
